@@ -1,0 +1,527 @@
+// rtclj_abi.cu -- the C ABI (include/rtclj_b200.h) over the sm_100a kernels.
+// Host side of the render loop: scene preparation (fp64 tables + the inflated fp32 cull
+// table), work-unit sizing, launches, copies.  No CPU fallback anywhere in this file.
+#include "../../include/rtclj_b200.h"
+#include "rtclj_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace rtclj;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver            \
+                      ? RTCLJ_E_NO_DEVICE : RTCLJ_E_CUDA,                                 \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+float round_up_to_float(double v) {
+  float f = (float)v;
+  if ((double)f < v) f = std::nextafterf(f, INFINITY);
+  return f;
+}
+
+}  // namespace
+
+struct rtclj_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  int n = 0, nquads = 0;
+  double shift[3] = {0, 0, 0};
+  DevBuf<float4> geom32;
+  DevBuf<Geom64> geom64;
+  DevBuf<MatRec> mat;
+  DevBuf<double> partial;
+  DevBuf<unsigned long long> counters;  // [0] queue, [1..4] stats
+  DevBuf<unsigned short> stack;
+  DevBuf<double> out_linear;            // used by the host-buffer entry points
+  DevBuf<unsigned char> out_rgb8;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int last_spu = 0;
+  bool have_scene = false;
+};
+
+namespace {
+
+size_t smem_needed(int nquads) {
+  return (size_t)nquads * 64 + (size_t)kListCap * kThreads * 2 + 16;
+}
+
+int local_rows_of(int H, int shard_index, int shard_count, int shard_rows) {
+  if (shard_count <= 1) return H;
+  int rows = 0;
+  const int ntiles = (H + shard_rows - 1) / shard_rows;
+  for (int t = shard_index; t < ntiles; t += shard_count)
+    rows += std::min(shard_rows, H - t * shard_rows);
+  return rows;
+}
+
+// Unit size chosen from the image alone (not from the GPU count), so that an image is
+// bit-identical however many GPUs share it: aim at >= 32 units per lane of an 8-GPU box.
+int auto_samples_per_unit(int W, int H, int spp) {
+  const double want_units = 32.0 * 148.0 * kThreads * 8.0;
+  const double pixels = (double)W * (double)H;
+  int nchunks = (int)std::ceil(want_units / pixels);
+  nchunks = std::max(1, std::min(nchunks, std::max(1, spp / 8)));
+  return (spp + nchunks - 1) / nchunks;
+}
+
+int validate(const rtclj_camera* cam, const rtclj_params* prm) {
+  if (!cam || !prm) return fail(RTCLJ_E_INVALID, "null camera or params");
+  if (cam->width <= 0 || cam->height <= 0) return fail(RTCLJ_E_INVALID, "image size must be positive");
+  if ((uint64_t)cam->width * (uint64_t)cam->height > 0xffffffffull)
+    return fail(RTCLJ_E_INVALID, "more than 2^32 pixels");
+  if (prm->spp <= 0) return fail(RTCLJ_E_INVALID, "spp must be positive");
+  if (prm->shard_count > 1 && (prm->shard_index < 0 || prm->shard_index >= prm->shard_count || prm->shard_rows <= 0))
+    return fail(RTCLJ_E_INVALID, "bad shard (%d of %d, %d rows)", prm->shard_index, prm->shard_count, prm->shard_rows);
+  return RTCLJ_OK;
+}
+
+}  // namespace
+
+// ---- arithmetic-peak calibration (pure FMA loops, 8 independent chains per thread)
+namespace {
+template <int MODE>
+__global__ void __launch_bounds__(512) peak_kernel(float* out, int iters, float seed) {
+  if (MODE == 2) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7);
+  } else if (MODE == 1) {
+    f32x2 a0 = splat2(seed), a1 = splat2(seed + 1), a2 = splat2(seed + 2), a3 = splat2(seed + 3);
+    f32x2 a4 = splat2(seed + 4), a5 = splat2(seed + 5), a6 = splat2(seed + 6), a7 = splat2(seed + 7);
+    const f32x2 m = splat2(0.999999f), c = splat2(1e-9f);
+    for (int i = 0; i < iters; ++i) {
+      a0 = fma2(a0, m, c); a1 = fma2(a1, m, c); a2 = fma2(a2, m, c); a3 = fma2(a3, m, c);
+      a4 = fma2(a4, m, c); a5 = fma2(a5, m, c); a6 = fma2(a6, m, c); a7 = fma2(a7, m, c);
+    }
+    float lo, hi, s = 0.f;
+    unpack2(a0, lo, hi); s += lo + hi; unpack2(a1, lo, hi); s += lo + hi; unpack2(a2, lo, hi); s += lo + hi;
+    unpack2(a3, lo, hi); s += lo + hi; unpack2(a4, lo, hi); s += lo + hi; unpack2(a5, lo, hi); s += lo + hi;
+    unpack2(a6, lo, hi); s += lo + hi; unpack2(a7, lo, hi); s += lo + hi;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  } else {
+    float a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const float m = 0.999999f, c = 1e-9f;
+    for (int i = 0; i < iters; ++i) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  }
+}
+}  // namespace
+
+
+extern "C" {
+
+int rtclj_abi_version(void) { return RTCLJ_ABI_VERSION; }
+const char* rtclj_last_error(void) { return g_err.c_str(); }
+
+int rtclj_device_count(int* count) {
+  if (!count) return fail(RTCLJ_E_INVALID, "null count");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return fail(RTCLJ_E_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e)); }
+  *count = n;
+  return RTCLJ_OK;
+}
+
+int rtclj_ctx_create(int32_t device, rtclj_ctx** out) {
+  if (!out) return fail(RTCLJ_E_INVALID, "null out");
+  *out = nullptr;
+  int ndev = 0;
+  int rc = rtclj_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev == 0) return fail(RTCLJ_E_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(RTCLJ_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(RTCLJ_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  rtclj_ctx* c = new rtclj_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CU(c->counters.reserve(8));
+  CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  *out = c;
+  return RTCLJ_OK;
+}
+
+void rtclj_ctx_destroy(rtclj_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  c->geom32.release(); c->geom64.release(); c->mat.release(); c->partial.release();
+  c->counters.release(); c->stack.release(); c->out_linear.release(); c->out_rgb8.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
+  if (!c || !s) return fail(RTCLJ_E_INVALID, "null ctx or scene");
+  const int n = s->n;
+  if (n < 0) return fail(RTCLJ_E_INVALID, "negative sphere count");
+  if (n > 0 && (!s->center_xyz || !s->radius || !s->material || !s->albedo_rgb || !s->fuzz || !s->ior))
+    return fail(RTCLJ_E_INVALID, "null scene array");
+  if (n > 65532) return fail(RTCLJ_E_TOO_LARGE, "%d spheres: survivor lists hold 16-bit indices", n);
+  const int nquads = (n + 3) / 4;
+  if (smem_needed(nquads) > c->smem_optin)
+    return fail(RTCLJ_E_TOO_LARGE, "%d spheres need %zu B of shared memory, device offers %zu", n,
+                smem_needed(nquads), c->smem_optin);
+  for (int i = 0; i < n; ++i) {
+    const int k = s->material[i];
+    if (k != RTCLJ_LAMBERTIAN && k != RTCLJ_METAL && k != RTCLJ_DIELECTRIC)
+      return fail(RTCLJ_E_INVALID, "sphere %d: unknown material id %d", i, k);
+  }
+  CU(cudaSetDevice(c->device));
+
+  // translation for the fp32 cull: per-axis median of the centres keeps |C - shift|
+  // (and with it the inflation of the conservative test) small where the spheres are
+  double shift[3] = {0, 0, 0};
+  if (n > 0) {
+    std::vector<double> tmp((size_t)n);
+    for (int a = 0; a < 3; ++a) {
+      for (int i = 0; i < n; ++i) tmp[(size_t)i] = s->center_xyz[3 * i + a];
+      std::nth_element(tmp.begin(), tmp.begin() + n / 2, tmp.end());
+      shift[a] = tmp[(size_t)(n / 2)];
+    }
+  }
+  std::vector<Geom64> g64((size_t)std::max(n, 1));
+  std::vector<MatRec> mats((size_t)std::max(n, 1));
+  std::vector<float> g32((size_t)std::max(nquads, 1) * 16);
+  for (int i = 0; i < nquads * 4; ++i) {
+    float cx = 0.f, cy = 0.f, cz = 0.f, r2s = -1e30f;  // padding never survives the cull
+    if (i < n) {
+      const double* C = s->center_xyz + 3 * i;
+      const double r = s->radius[i];
+      g64[(size_t)i] = Geom64{C[0], C[1], C[2], r};
+      MatRec m;
+      m.albedo[0] = s->albedo_rgb[3 * i]; m.albedo[1] = s->albedo_rgb[3 * i + 1]; m.albedo[2] = s->albedo_rgb[3 * i + 2];
+      m.kind = s->material[i];
+      m.param = m.kind == RTCLJ_METAL ? s->fuzz[i] : s->ior[i];
+      m.pad = 0;
+      mats[(size_t)i] = m;
+      cx = (float)(C[0] - shift[0]); cy = (float)(C[1] - shift[1]); cz = (float)(C[2] - shift[2]);
+      const double mc = std::max(std::fabs((double)cx), std::max(std::fabs((double)cy), std::fabs((double)cz)));
+      const double eps = (double)kEps32;
+      r2s = round_up_to_float(r * r * (1.0 + 8.0 * eps) + 32.0 * eps * mc * mc);
+    }
+    // pair-packed: pair p = i/2, half h = i&1 -> {cx[h], cy[2+h]} in vec0, {cz[h], r2s[2+h]} in vec1
+    const int p = i >> 1, h = i & 1;
+    float* v = g32.data() + (size_t)p * 8;
+    v[0 + h] = cx; v[2 + h] = cy; v[4 + h] = cz; v[6 + h] = r2s;
+  }
+  CU(c->geom64.reserve((size_t)std::max(n, 1)));
+  CU(c->mat.reserve((size_t)std::max(n, 1)));
+  CU(c->geom32.reserve((size_t)std::max(nquads, 1) * 4));
+  if (n > 0) {
+    CU(cudaMemcpy(c->geom64.p, g64.data(), sizeof(Geom64) * (size_t)n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->mat.p, mats.data(), sizeof(MatRec) * (size_t)n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->geom32.p, g32.data(), sizeof(float) * 16 * (size_t)nquads, cudaMemcpyHostToDevice));
+  }
+  c->n = n; c->nquads = nquads;
+  std::memcpy(c->shift, shift, sizeof shift);
+  c->have_scene = true;
+  return RTCLJ_OK;
+}
+
+int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* prm, void* d_out_linear,
+                     void* d_out_rgb8, void* stream_) {
+  if (!c) return fail(RTCLJ_E_INVALID, "null ctx");
+  if (!c->have_scene) return fail(RTCLJ_E_INVALID, "rtclj_ctx_set_scene has not been called");
+  int rc = validate(cam, prm);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CU(cudaSetDevice(c->device));
+
+  const int W = cam->width, H = cam->height;
+  const int shard_count = prm->shard_count > 1 ? prm->shard_count : 1;
+  const int shard_index = shard_count > 1 ? prm->shard_index : 0;
+  const int shard_rows = shard_count > 1 ? prm->shard_rows : H;
+  const int local_rows = local_rows_of(H, shard_index, shard_count, shard_rows);
+  int spu = prm->samples_per_unit > 0 ? prm->samples_per_unit : auto_samples_per_unit(W, H, prm->spp);
+  if (spu > prm->spp) spu = prm->spp;
+  const int nchunks = (prm->spp + spu - 1) / spu;
+  const unsigned long long local_pixels = (unsigned long long)local_rows * (unsigned long long)W;
+  const unsigned long long total_units = local_pixels * (unsigned long long)nchunks;
+  c->last_spu = spu;
+
+  CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), stream));
+  if (total_units == 0) return RTCLJ_OK;
+  CU(c->partial.reserve((size_t)total_units * 3));
+
+  const int grid = c->sm_count;
+  const bool run_kernel = prm->max_depth > 0;
+  CU(cudaEventRecord(c->ev0, stream));
+  if (!run_kernel) {
+    CU(cudaMemsetAsync(c->partial.p, 0, (size_t)total_units * 3 * sizeof(double), stream));  // depth <= 0: black
+  } else {
+    KParams P;
+    std::memset(&P, 0, sizeof P);
+    for (int a = 0; a < 3; ++a) {
+      P.p00[a] = cam->pixel00[a]; P.du[a] = cam->pixel_du[a]; P.dv[a] = cam->pixel_dv[a];
+      P.center[a] = cam->center[a]; P.ddu[a] = cam->defocus_u[a]; P.ddv[a] = cam->defocus_v[a];
+      P.shift[a] = c->shift[a];
+    }
+    P.use_defocus = !(cam->defocus_angle <= 0.0);
+    P.W = W; P.H = H; P.spp = prm->spp; P.max_depth = prm->max_depth;
+    P.flags = prm->flags; P.k0 = (unsigned)prm->seed; P.k1 = (unsigned)(prm->seed >> 32);
+    P.n = c->n; P.nquads = c->nquads; P.geom_bytes = (unsigned)c->nquads * 64u;
+    P.shard_index = shard_index; P.shard_count = shard_count; P.shard_rows = shard_rows;
+    P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
+    P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
+    P.partial = c->partial.p; P.queue = c->counters.p; P.stats = c->counters.p + 1;
+    P.stack_stride = (unsigned)grid * kThreads;
+    if (prm->flags & RTCLJ_F_REVERSE_PRODUCT) {
+      CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
+      P.stack = c->stack.p;
+    }
+    const size_t smem = smem_needed(c->nquads);
+    render_kernel<<<grid, kThreads, smem, stream>>>(P);
+    CU(cudaGetLastError());
+  }
+  FParams F;
+  F.partial = c->partial.p; F.out_linear = (double*)d_out_linear; F.out_rgb8 = (unsigned char*)d_out_rgb8;
+  F.W = W; F.spp = prm->spp; F.nchunks = nchunks;
+  F.shard_index = shard_index; F.shard_count = shard_count; F.shard_rows = shard_rows;
+  F.flags = prm->flags; F.local_pixels = local_pixels;
+  if (d_out_linear || d_out_rgb8) {
+    const unsigned blocks = (unsigned)((local_pixels + 255) / 256);
+    finalize_kernel<<<blocks, 256, 0, stream>>>(F);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(c->ev1, stream));
+  return RTCLJ_OK;
+}
+
+int rtclj_ctx_stats(rtclj_ctx* c, void* stream_, rtclj_stats* st) {
+  if (!c || !st) return fail(RTCLJ_E_INVALID, "null ctx or stats");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize((cudaStream_t)stream_));
+  unsigned long long h[8];
+  CU(cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+  std::memset(st, 0, sizeof *st);
+  st->samples = h[1]; st->segments = h[2]; st->exact_tests = h[3]; st->list_overflows = h[4];
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) st->device_ms = ms; else cudaGetLastError();
+  st->samples_per_unit = c->last_spu;
+  st->n_devices = 1;
+  return RTCLJ_OK;
+}
+
+// Copies the rows a shard owns from the device images to the host images.
+static int download_rows(rtclj_ctx* c, const rtclj_camera* cam, int shard_index, int shard_count,
+                         int shard_rows, double* out_linear, uint8_t* out_rgb8, cudaStream_t stream) {
+  const int W = cam->width, H = cam->height;
+  if (shard_count <= 1) { shard_index = 0; shard_rows = H; shard_count = 1; }
+  const int ntiles = (H + shard_rows - 1) / shard_rows;
+  for (int t = shard_index; t < ntiles; t += shard_count) {
+    const size_t row0 = (size_t)t * shard_rows;
+    const size_t rows = std::min((size_t)shard_rows, (size_t)H - row0);
+    const size_t off = row0 * W * 3, cnt = rows * W * 3;
+    if (out_linear) CU(cudaMemcpyAsync(out_linear + off, c->out_linear.p + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (out_rgb8) CU(cudaMemcpyAsync(out_rgb8 + off, c->out_rgb8.p + off, cnt, cudaMemcpyDeviceToHost, stream));
+  }
+  return RTCLJ_OK;
+}
+
+namespace {
+std::mutex g_ctx_mu;
+std::vector<rtclj_ctx*> g_ctx_cache;  // one cached context per device for the host-buffer calls
+
+int cached_ctx(int device, rtclj_ctx** out) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if ((int)g_ctx_cache.size() <= device) g_ctx_cache.resize((size_t)device + 1, nullptr);
+  if (!g_ctx_cache[(size_t)device]) {
+    int rc = rtclj_ctx_create(device, &g_ctx_cache[(size_t)device]);
+    if (rc) return rc;
+  }
+  *out = g_ctx_cache[(size_t)device];
+  return RTCLJ_OK;
+}
+}  // namespace
+
+int rtclj_render_multi(const rtclj_scene* scene, const rtclj_camera* cam, const rtclj_params* prm,
+                       const int32_t* devices, int32_t n_devices, double* out_linear, uint8_t* out_rgb8,
+                       rtclj_stats* stats) {
+  const auto t0 = std::chrono::steady_clock::now();
+  if (!scene) return fail(RTCLJ_E_INVALID, "null scene");
+  int rc = validate(cam, prm);
+  if (rc) return rc;
+  if (n_devices <= 0 || !devices) return fail(RTCLJ_E_INVALID, "empty device list");
+  int ndev = 0;
+  rc = rtclj_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev == 0) return fail(RTCLJ_E_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+  static std::mutex render_mu;  // the cached contexts are shared: one host-buffer render at a time
+  std::lock_guard<std::mutex> lk(render_mu);
+
+  const size_t npix = (size_t)cam->width * (size_t)cam->height;
+  std::vector<rtclj_ctx*> ctxs((size_t)n_devices);
+  rtclj_params p = *prm;
+  const bool single = n_devices == 1;
+  if (!single) {
+    p.shard_count = n_devices;
+    p.shard_rows = prm->shard_rows > 0 ? prm->shard_rows : 4;
+  }
+  for (int d = 0; d < n_devices; ++d) {
+    rc = cached_ctx(devices[d], &ctxs[(size_t)d]);
+    if (rc) return rc;
+    rtclj_ctx* c = ctxs[(size_t)d];
+    rc = rtclj_ctx_set_scene(c, scene);
+    if (rc) return rc;
+    if (out_linear) CU(c->out_linear.reserve(npix * 3));
+    if (out_rgb8) CU(c->out_rgb8.reserve(npix * 3));
+  }
+  for (int d = 0; d < n_devices; ++d) {  // enqueue everything, then wait: devices overlap
+    rtclj_ctx* c = ctxs[(size_t)d];
+    if (!single) p.shard_index = d;
+    rc = rtclj_ctx_render(c, cam, &p, out_linear ? c->out_linear.p : nullptr,
+                          out_rgb8 ? c->out_rgb8.p : nullptr, c->own_stream);
+    if (rc) return rc;
+    rc = download_rows(c, cam, p.shard_index, p.shard_count, p.shard_rows, out_linear, out_rgb8, c->own_stream);
+    if (rc) return rc;
+  }
+  rtclj_stats total;
+  std::memset(&total, 0, sizeof total);
+  for (int d = 0; d < n_devices; ++d) {
+    rtclj_stats s;
+    rc = rtclj_ctx_stats(ctxs[(size_t)d], ctxs[(size_t)d]->own_stream, &s);
+    if (rc) return rc;
+    total.samples += s.samples; total.segments += s.segments; total.exact_tests += s.exact_tests;
+    total.list_overflows += s.list_overflows;
+    total.device_ms = std::max(total.device_ms, s.device_ms);
+    total.samples_per_unit = s.samples_per_unit;
+  }
+  total.n_devices = n_devices;
+  total.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = total;
+  return RTCLJ_OK;
+}
+
+int rtclj_render(const rtclj_scene* scene, const rtclj_camera* cam, const rtclj_params* prm, double* out_linear,
+                 uint8_t* out_rgb8, rtclj_stats* stats) {
+  if (!prm) return fail(RTCLJ_E_INVALID, "null params");
+  if (prm->shard_count > 1) {
+    // one shard of the image on one device (one-process-per-GPU hosts)
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!scene) return fail(RTCLJ_E_INVALID, "null scene");
+    int rc = validate(cam, prm);
+    if (rc) return rc;
+    rtclj_ctx* c = nullptr;
+    rc = cached_ctx(prm->device, &c);
+    if (rc) return rc;
+    rc = rtclj_ctx_set_scene(c, scene);
+    if (rc) return rc;
+    const size_t npix = (size_t)cam->width * (size_t)cam->height;
+    if (out_linear) CU(c->out_linear.reserve(npix * 3));
+    if (out_rgb8) CU(c->out_rgb8.reserve(npix * 3));
+    rc = rtclj_ctx_render(c, cam, prm, out_linear ? c->out_linear.p : nullptr, out_rgb8 ? c->out_rgb8.p : nullptr, c->own_stream);
+    if (rc) return rc;
+    rc = download_rows(c, cam, prm->shard_index, prm->shard_count, prm->shard_rows, out_linear, out_rgb8, c->own_stream);
+    if (rc) return rc;
+    rtclj_stats s;
+    rc = rtclj_ctx_stats(c, c->own_stream, &s);
+    if (rc) return rc;
+    s.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = s;
+    return RTCLJ_OK;
+  }
+  const int32_t dev = prm->device;
+  return rtclj_render_multi(scene, cam, prm, &dev, 1, out_linear, out_rgb8, stats);
+}
+
+int rtclj_calibrate_peaks(int32_t device, double* ffma, double* ffma2, double* dfma, int32_t* sm_count) {
+  int ndev = 0;
+  int rc = rtclj_device_count(&ndev);
+  if (rc) return rc;
+  if (device < 0 || device >= ndev) return fail(RTCLJ_E_INVALID, "device %d out of range", device);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int sms = prop.multiProcessorCount;
+  if (sm_count) *sm_count = sms;
+  const int blocks = sms * 4, threads = 512, iters = 1 << 14;
+  float* out = nullptr;
+  CU(cudaMalloc(&out, sizeof(float) * (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double res[3] = {0, 0, 0};
+  for (int mode = 0; mode < 3; ++mode) {
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      CU(cudaEventRecord(e0));
+      if (mode == 0) peak_kernel<0><<<blocks, threads>>>(out, iters, 1.0f);
+      else if (mode == 1) peak_kernel<1><<<blocks, threads>>>(out, iters, 1.0f);
+      else peak_kernel<2><<<blocks, threads>>>(out, iters / 2, 1.0f);
+      CU(cudaEventRecord(e1));
+      CU(cudaEventSynchronize(e1));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, e0, e1));
+      const double fmas = (double)blocks * threads * 8.0 * (mode == 2 ? iters / 2 : iters) * (mode == 1 ? 2.0 : 1.0);
+      const double tf = 2.0 * fmas / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best) best = tf;
+    }
+    res[mode] = best;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  if (ffma) *ffma = res[0];
+  if (ffma2) *ffma2 = res[1];
+  if (dfma) *dfma = res[2];
+  return RTCLJ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// rtclj_host.cpp -- host-only entry points of the C ABI: the steps either side of the
+// render loop: quantisation + P3 encoding after it, camera derivation
+// and scene generation before it.  Plain C++17, IEEE double, compiled with
+// -ffp-contract=off so the arithmetic is what the JVM (and camera.py) computes.
+#include "../../include/rtclj_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+namespace {
+
+struct V { double x, y, z; };
+inline V mk(double x, double y, double z) { return V{x, y, z}; }
+inline V ld(const double* p) { return V{p[0], p[1], p[2]}; }
+inline void st(double* p, V v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+inline V add(V a, V b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V sub(V a, V b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V muls(V a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
+inline V divs(V a, double s) { return mk(a.x / s, a.y / s, a.z / s); }
+inline V neg(V a) { return mk(-a.x, -a.y, -a.z); }
+inline V cross(V u, V v) {  // vec3a.clj:64-67
+  return mk(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+}
+inline double length(V a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline V unit(V a) { return divs(a, length(a)); }
+inline double deg_to_rad(double d) { return d * M_PI / 180.0; }  // raytracing.clj:60-61
+
+int64_t gcd64(int64_t a, int64_t b) {
+  while (b) { int64_t t = a % b; a = b; b = t; }
+  return a < 0 ? -a : a;
+}
+
+inline int quantise(double c, bool linear) {  // write-color!, raytracing.clj:19-26
+  double v;
+  if (linear) {
+    v = 255.999 * c;
+  } else {
+    double g = c > 0.0 ? std::sqrt(c) : 0.0;
+    double lo = g > 0.0 ? g : 0.0;
+    double cl = lo < 0.999 ? lo : 0.999;
+    v = 256.0 * cl;
+  }
+  return (v != v) ? 0 : (int)v;
+}
+
+struct SplitMix64 {
+  uint64_t s;
+  uint64_t next() {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+  double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int rtclj_quantise_rgb8(const double* linear, size_t n_values, uint32_t flags, uint8_t* out) {
+  if ((!linear || !out) && n_values) return RTCLJ_E_INVALID;
+  const bool lin = (flags & RTCLJ_F_QUANT_LINEAR) != 0;
+  for (size_t i = 0; i < n_values; ++i) out[i] = (uint8_t)quantise(linear[i], lin);
+  return RTCLJ_OK;
+}
+
+int rtclj_encode_ppm_p3(const uint8_t* rgb8, int32_t width, int32_t height, char* out, size_t capacity,
+                        size_t* len) {
+  if (width <= 0 || height <= 0 || !len) return RTCLJ_E_INVALID;
+  char header[64];
+  const int hl = std::snprintf(header, sizeof header, "P3\n%d %d\n255\n", width, height);
+  const size_t npix = (size_t)width * (size_t)height;
+  if (!out) {  // sizing call: worst case "255 255 255\n"
+    *len = (size_t)hl + npix * 12;
+    return RTCLJ_OK;
+  }
+  if (!rgb8) return RTCLJ_E_INVALID;
+  static const struct Lut { char s[256][4]; unsigned char n[256]; Lut() {
+      for (int v = 0; v < 256; ++v) n[v] = (unsigned char)std::snprintf(s[v], 4, "%d", v);
+    } } lut;
+  size_t need = (size_t)hl;
+  for (size_t i = 0; i < npix * 3; ++i) need += lut.n[rgb8[i]] + 1u;
+  *len = need;
+  if (need > capacity) return RTCLJ_E_BUFFER;
+  std::memcpy(out, header, (size_t)hl);
+  char* w = out + hl;
+  for (size_t p = 0; p < npix; ++p) {
+    for (int ch = 0; ch < 3; ++ch) {
+      const unsigned v = rgb8[3 * p + ch];
+      const unsigned n = lut.n[v];
+      w[0] = lut.s[v][0]; if (n > 1) w[1] = lut.s[v][1]; if (n > 2) w[2] = lut.s[v][2];
+      w += n;
+      *w++ = ch == 2 ? '\n' : ' ';
+    }
+  }
+  return RTCLJ_OK;
+}
+
+// clojure.lang.Ratio.doubleValue: BigDecimal(num).divide(BigDecimal(den), DECIMAL64).doubleValue(),
+// i.e. the quotient rounded HALF_EVEN to 16 significant decimal digits, then to double
+// (SURVEY.md Appendix B.1).  Integral quotients are Longs in Clojure and stay exact.
+double rtclj_ratio_to_double(int64_t num, int64_t den) {
+  if (den == 0) return num == 0 ? NAN : (num > 0 ? INFINITY : -INFINITY);
+  const int64_t g = gcd64(num, den);
+  if (g) { num /= g; den /= g; }
+  if (den < 0) { num = -num; den = -den; }
+  if (den == 1) return (double)num;
+  const bool negative = num < 0;
+  unsigned __int128 n = (unsigned __int128)(negative ? -(__int128)num : (__int128)num);
+  const unsigned __int128 d = (unsigned __int128)den;
+  unsigned __int128 ip = n / d, rem = n % d;
+  std::string digits;  // significant digits, no leading zeros
+  int exp10 = 0;       // value = 0.DIGITS * 10^exp10
+  if (ip > 0) {
+    std::string s;
+    while (ip > 0) { s.insert(s.begin(), (char)('0' + (int)(ip % 10))); ip /= 10; }
+    digits = s;
+    exp10 = (int)s.size();
+  }
+  while ((int)digits.size() < 17 && (rem != 0 || !digits.empty())) {
+    rem *= 10;
+    const int q = (int)(rem / d);
+    rem %= d;
+    if (digits.empty() && q == 0) { exp10--; continue; }
+    digits.push_back((char)('0' + q));
+    if (rem == 0 && (int)digits.size() >= 17) break;
+    if (rem == 0) break;
+  }
+  if ((int)digits.size() > 16) {  // round half-even at 16 digits
+    const int guard = digits[16] - '0';
+    const bool sticky = rem != 0;
+    digits.resize(16);
+    bool up = guard > 5 || (guard == 5 && (sticky || ((digits[15] - '0') & 1)));
+    if (up) {
+      int i = 15;
+      while (i >= 0 && digits[(size_t)i] == '9') { digits[(size_t)i] = '0'; --i; }
+      if (i >= 0) digits[(size_t)i]++;
+      else { digits.insert(digits.begin(), '1'); digits.resize(16); exp10++; }
+    }
+  }
+  const std::string text = std::string(negative ? "-" : "") + "0." + digits + "e" + std::to_string(exp10);
+  return std::strtod(text.c_str(), nullptr);
+}
+
+// raytracing.clj:105-139
+int rtclj_camera_main(int32_t width, int32_t height, double vfov, const double look_from[3],
+                      const double look_at[3], const double vup[3], double defocus_angle, double focus_dist,
+                      rtclj_camera* out) {
+  if (!out || !look_from || !look_at || !vup || width <= 0 || height <= 0) return RTCLJ_E_INVALID;
+  const double theta = deg_to_rad(vfov);
+  const double h = std::tan(theta / 2);
+  const double viewport_height = 2.0 * h * focus_dist;
+  const double viewport_width = viewport_height * rtclj_ratio_to_double(width, height);
+  const V w = unit(sub(ld(look_from), ld(look_at)));
+  const V u = unit(cross(ld(vup), w));
+  const V v = cross(w, u);
+  const V center = ld(look_from);
+  const V viewport_u = muls(u, viewport_width);
+  const V viewport_v = muls(neg(v), viewport_height);
+  const V du = divs(viewport_u, (double)width);
+  const V dv = divs(viewport_v, (double)height);
+  const V upper_left = sub(sub(sub(center, muls(w, focus_dist)), divs(viewport_u, 2.0)), divs(viewport_v, 2.0));
+  const V p00 = add(upper_left, muls(add(du, dv), 0.5));
+  const double defocus_radius = focus_dist * std::tan(deg_to_rad(defocus_angle / 2.0));
+  st(out->pixel00, p00); st(out->pixel_du, du); st(out->pixel_dv, dv); st(out->center, center);
+  st(out->defocus_u, muls(u, defocus_radius)); st(out->defocus_v, muls(v, defocus_radius));
+  out->defocus_angle = defocus_angle;
+  out->width = width; out->height = height;
+  return RTCLJ_OK;
+}
+
+// realm/raytracing.clj:264-280, 306-322
+int rtclj_camera_realm(int32_t width, int32_t height, double vfov, const double look_from[3],
+                       const double look_at[3], const double vup[3], rtclj_camera* out) {
+  if (!out || !look_from || !look_at || !vup || width <= 0 || height <= 0) return RTCLJ_E_INVALID;
+  const V temp = sub(ld(look_from), ld(look_at));
+  const double focal = length(temp);
+  const V w = divs(temp, focal);
+  const V u = unit(cross(ld(vup), w));
+  const V v = cross(w, u);
+  const double theta = deg_to_rad(vfov);
+  const double h = std::tan(theta / 2.0);
+  const double viewport_height = 2.0 * h * focal;
+  const double viewport_width = viewport_height * ((double)width / (double)height);
+  const V viewport_u = muls(u, viewport_width);
+  const V viewport_v = muls(v, -viewport_height);
+  const V du = divs(viewport_u, (double)width);
+  const V dv = divs(viewport_v, (double)height);
+  V ul = sub(ld(look_from), muls(w, focal));
+  ul = sub(ul, divs(viewport_u, 2.0));
+  ul = sub(ul, divs(viewport_v, 2.0));
+  st(out->pixel00, add(ul, divs(add(du, dv), 2.0)));
+  st(out->pixel_du, du); st(out->pixel_dv, dv); st(out->center, ld(look_from));
+  st(out->defocus_u, mk(0, 0, 0)); st(out->defocus_v, mk(0, 0, 0));
+  out->defocus_angle = 0.0;
+  out->width = width; out->height = height;
+  return RTCLJ_OK;
+}
+
+// experimental/raytracing_i.clj:82-90, 127-144
+int rtclj_camera_i(int32_t width, int32_t height, rtclj_camera* out) {
+  if (!out || width <= 0 || height <= 0) return RTCLJ_E_INVALID;
+  const double focal_length = 1.0, viewport_height = 2.0;
+  const double viewport_width = viewport_height * rtclj_ratio_to_double(width, height);
+  const V center = mk(0, 0, 0);
+  const V viewport_u = mk(viewport_width, 0.0, 0.0);
+  const V viewport_v = mk(0.0, -viewport_height, 0.0);
+  const V du = divs(viewport_u, (double)width);
+  const V dv = divs(viewport_v, (double)height);
+  V ul = sub(center, mk(0.0, 0.0, focal_length));
+  ul = sub(ul, divs(viewport_u, 2.0));
+  ul = sub(ul, divs(viewport_v, 2.0));
+  st(out->pixel00, add(ul, divs(add(du, dv), 2.0)));
+  st(out->pixel_du, du); st(out->pixel_dv, dv); st(out->center, center);
+  st(out->defocus_u, mk(0, 0, 0)); st(out->defocus_v, mk(0, 0, 0));
+  out->defocus_angle = 0.0;
+  out->width = width; out->height = height;
+  return RTCLJ_OK;
+}
+
+// The book's random-sphere field; same draws as scenes.py.
+int rtclj_scene_random_field(uint64_t seed, int32_t lo, int32_t hi, int32_t cap, double* center_xyz,
+                             double* radius, int32_t* material, double* albedo_rgb, double* fuzz, double* ior,
+                             int32_t* n_out) {
+  if (!n_out || hi < lo) return RTCLJ_E_INVALID;
+  const bool write = cap > 0;
+  if (write && (!center_xyz || !radius || !material || !albedo_rgb || !fuzz || !ior)) return RTCLJ_E_INVALID;
+  int n = 0;
+  bool overflow = false;
+  auto put = [&](double cx, double cy, double cz, double r, int kind, double ar, double ag, double ab, double fz,
+                 double ri) {
+    if (write) {
+      if (n >= cap) { overflow = true; ++n; return; }
+      center_xyz[3 * n] = cx; center_xyz[3 * n + 1] = cy; center_xyz[3 * n + 2] = cz;
+      radius[n] = r; material[n] = kind;
+      albedo_rgb[3 * n] = ar; albedo_rgb[3 * n + 1] = ag; albedo_rgb[3 * n + 2] = ab;
+      fuzz[n] = fz; ior[n] = ri;
+    }
+    ++n;
+  };
+  SplitMix64 rng{seed};
+  put(0.0, -1000.0, 0.0, 1000.0, RTCLJ_LAMBERTIAN, 0.5, 0.5, 0.5, 0.0, 1.0);
+  for (int a = lo; a < hi; ++a) {
+    for (int b = lo; b < hi; ++b) {
+      const double choose = rng.uniform();
+      const double cx = (double)a + 0.9 * rng.uniform();
+      const double cz = (double)b + 0.9 * rng.uniform();
+      double d[7];
+      for (double& x : d) x = rng.uniform();
+      const double dx = cx - 4.0, dz = cz - 0.0;
+      if (std::sqrt(dx * dx + dz * dz) <= 0.9) continue;
+      if (choose < 0.8) put(cx, 0.2, cz, 0.2, RTCLJ_LAMBERTIAN, d[0] * d[1], d[2] * d[3], d[4] * d[5], 0.0, 1.0);
+      else if (choose < 0.95)
+        put(cx, 0.2, cz, 0.2, RTCLJ_METAL, 0.5 + 0.5 * d[0], 0.5 + 0.5 * d[1], 0.5 + 0.5 * d[2], 0.5 * d[3], 1.0);
+      else put(cx, 0.2, cz, 0.2, RTCLJ_DIELECTRIC, 1.0, 1.0, 1.0, 0.0, 1.5);
+    }
+  }
+  put(0.0, 1.0, 0.0, 1.0, RTCLJ_DIELECTRIC, 1.0, 1.0, 1.0, 0.0, 1.5);
+  put(-4.0, 1.0, 0.0, 1.0, RTCLJ_LAMBERTIAN, 0.4, 0.2, 0.1, 0.0, 1.0);
+  put(4.0, 1.0, 0.0, 1.0, RTCLJ_METAL, 0.7, 0.6, 0.5, 0.0, 1.0);
+  *n_out = n;
+  return overflow ? RTCLJ_E_BUFFER : RTCLJ_OK;
+}
+
+}  // extern "C"

@@ -75,7 +75,8 @@ def _random_field(seed: int, lo: int, hi: int) -> List[dict]:
             cz = b + 0.9 * rng.uniform()
             # every candidate consumes the same number of draws, kept or not
             d = [rng.uniform() for _ in range(7)]
-            if math.sqrt((cx - 4.0) ** 2 + (cz - 0.0) ** 2) <= 0.9:
+            dx, dz = cx - 4.0, cz - 0.0
+            if math.sqrt(dx * dx + dz * dz) <= 0.9:
                 continue
             geom = hittable.sphere((cx, 0.2, cz), 0.2)
             if choose < 0.8:

@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on
+the same Philox stream.  Bar: BIT-EXACT linear radiance (float64), 8-bit output and
+segment counts -- stricter than north_star's tolerance (>= 99.9 % of pixels within 1e-3),
+which the cull + fp64 design makes unnecessary.  Run with `pytest -m gpu` on a B200."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import raytracing_clj_b200 as R
+from raytracing_clj_b200 import _abi, render
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+S, CAM = R.scenes, R.camera
+
+
+def gpu(world, cam, spp, depth, **kw):
+    return render.render(world, cam, spp, depth, **kw)
+
+
+def assert_same(world, cam, spp, depth, seed, flags, unit=0, threads=8, **kw):
+    soa = S.to_soa(world)
+    lin_o, rgb_o, st_o = O.render(soa, cam, spp, depth, seed=seed, flags=flags, threads=threads,
+                                  samples_per_unit=unit if unit else spp)
+    lin_g, rgb_g, st_g = gpu(soa, cam, spp, depth, seed=seed, flags=flags,
+                             samples_per_unit=unit if unit else spp, **kw)
+    bad = np.argwhere(lin_o != lin_g)
+    assert bad.size == 0, (f"{len(bad)} of {lin_o.size} linear values differ; first {bad[0]}: "
+                           f"oracle {lin_o[tuple(bad[0])]!r} gpu {lin_g[tuple(bad[0])]!r}")
+    assert np.array_equal(rgb_o, rgb_g)
+    assert st_g["segments"] == st_o.segments and st_g["samples"] == st_o.samples
+    return st_g
+
+
+def test_library_loaded_and_device_present():
+    import ctypes as C
+    n = C.c_int()
+    _abi.check(_abi.lib().rtclj_device_count(C.byref(n)))
+    assert n.value >= 1
+
+
+def test_committed_fixtures_bit_exact():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    fx = np.load(os.path.join(GOLD, "oracle_fixtures.npz"))
+    for name, (bodies, cam, spp, depth, seed, flags, unit) in mg.fixture_cases().items():
+        lin, rgb, st = gpu(bodies, cam, spp, depth, seed=seed, flags=flags,
+                           samples_per_unit=unit if unit else spp)
+        assert np.array_equal(lin, fx[name + "/linear"]), name
+        assert np.array_equal(rgb, fx[name + "/rgb8"]), name
+        assert st["segments"] == int(fx[name + "/segments"][0]), name
+
+
+@pytest.mark.parametrize("variant", ["main", "realm", "i"])
+def test_reference_scenes_bit_exact(variant):
+    if variant == "main":
+        assert_same(S.main_hittables(), CAM.main_camera(200), 32, 50, 1, O.FLAGS_MAIN)
+    elif variant == "realm":
+        assert_same(S.realm_hittables(), CAM.realm_camera(200), 32, 50, 2, O.FLAGS_REALM)
+    else:
+        assert_same(S.i_hittables(), CAM.i_camera(200), 32, 50, 3, O.FLAGS_I)
+
+
+def test_config1_default_scene_statistics_vs_reference_render():
+    """BASELINE.json config 1 on the GPU: 400x225, 100 spp, depth 50 -- bit-exact vs the
+    oracle AND statistically consistent with the reference's committed scene.ppm."""
+    gold = np.load(os.path.join(GOLD, "reference_images.npz"))["scene_main"]
+    st = assert_same(S.main_hittables(), CAM.main_camera(), 100, 50, 1, O.FLAGS_MAIN)
+    _, rgb, _ = gpu(S.main_hittables(), CAM.main_camera(), 100, 50, seed=1, flags=O.FLAGS_MAIN,
+                    samples_per_unit=100)
+    assert np.all(np.abs(rgb.reshape(-1, 3).mean(0) - gold.reshape(-1, 3).mean(0)) < 0.1)
+    assert abs(st["segments"] / st["samples"] - 3.675) < 0.01
+
+
+def test_cover_scene_bit_exact():
+    world = S.cover_hittables(7)
+    assert 480 <= len(world) <= 488
+    st = assert_same(world, CAM.main_camera(160, 90, **S.COVER_CAMERA), 8, 50, 7, O.FLAGS_MAIN)
+    assert st["list_overflows"] == 0
+    # the cull must leave only a handful of fp64 tests per segment
+    assert st["exact_tests"] / st["segments"] < 12
+
+
+def test_ten_thousand_sphere_field_bit_exact():
+    world = S.field_hittables(7)
+    assert 9900 <= len(world) <= 10004
+    assert_same(world, CAM.main_camera(96, 54, **S.FIELD_CAMERA), 4, 50, 5, O.FLAGS_MAIN)
+
+
+def test_cull_equals_exhaustive_fp64_scan():
+    world = S.cover_hittables(3)
+    cam = CAM.main_camera(128, 72, **S.COVER_CAMERA)
+    a, ra, sa = gpu(world, cam, 8, 50, seed=9, flags=O.FLAGS_MAIN, samples_per_unit=8)
+    b, rb, sb = gpu(world, cam, 8, 50, seed=9, flags=O.FLAGS_MAIN | _abi.F_NO_CULL, samples_per_unit=8)
+    assert np.array_equal(a, b) and np.array_equal(ra, rb) and sa["segments"] == sb["segments"]
+    assert sb["exact_tests"] == sb["segments"] * len(world)
+
+
+def test_far_origin_and_huge_spheres():
+    """Numerics the survey flags (7.3-3): r = 1000 ground, rays leaving from far away."""
+    world = S.cover_hittables(5)
+    cam = CAM.main_camera(96, 54, vfov=40.0, look_from=(600.0, 30.0, 400.0), look_at=(0.0, 0.0, 0.0),
+                          defocus_angle=0.0, focus_dist=10.0)
+    assert_same(world, cam, 8, 50, 13, O.FLAGS_MAIN)
+
+
+def test_primary_ray_4k_bit_exact_8bit():
+    """BASELINE.json config 4 at full 3840x2160: (i) the raytracing-i normal-shading scene,
+    (ii) realm semantics at max-depth 1 on a camera that sees sky.  8-bit output bit-exact."""
+    cam = CAM.i_camera(3840)
+    assert (cam.width, cam.height) == (3840, 2160)
+    for world, flags, depth, seed in ((S.i_hittables(), O.FLAGS_I, 50, 4), (S.realm_hittables(), O.FLAGS_REALM, 1, 6)):
+        soa = S.to_soa(world)
+        lin_o, rgb_o, st_o = O.render(soa, cam, 4, depth, seed=seed, flags=flags, threads=8)
+        lin_g, rgb_g, st_g = gpu(soa, cam, 4, depth, seed=seed, flags=flags, samples_per_unit=4)
+        assert np.array_equal(rgb_o, rgb_g)
+        assert np.array_equal(lin_o, lin_g)
+        assert st_g["segments"] == st_o.segments == 3840 * 2160 * 4
+
+
+def test_edge_cases():
+    cam = CAM.realm_camera(32)
+    # empty hittable list: sky only
+    assert_same([], cam, 4, 50, 1, O.FLAGS_REALM)
+    # one sphere, one pixel, one sample
+    one = [S.body(R.hittable.sphere((0, 0, -1), 0.5), R.material.metal((0.9, 0.9, 0.9), 0.0))]
+    assert_same(one, CAM.i_camera(1, 1), 1, 50, 1, O.FLAGS_REALM)
+    # depth 0 -> black, nothing traced; depth 1 -> sky where the primary ray misses
+    lin, rgb, st = gpu(S.realm_hittables(), cam, 4, 0, flags=O.FLAGS_REALM)
+    assert not lin.any() and not rgb.any() and st["segments"] == 0
+    assert_same(S.realm_hittables(), CAM.i_camera(64), 4, 1, 2, O.FLAGS_REALM)
+    # ragged sizes: n not a multiple of 4, odd image sizes, spp not a multiple of the unit
+    for n in (1, 2, 3, 5, 6, 7):
+        world = S.cover_hittables(2)[:n]
+        assert_same(world, CAM.main_camera(37, 23, **S.COVER_CAMERA), 7, 50, n, O.FLAGS_MAIN, unit=3)
+    # concentric spheres and exact ties: the first body wins
+    tie = [S.body(R.hittable.sphere((0, 0, -1), 0.5), R.material.lambertian((0.9, 0.1, 0.1))),
+           S.body(R.hittable.sphere((0, 0, -1), 0.5), R.material.lambertian((0.1, 0.9, 0.1)))]
+    assert_same(tie, CAM.i_camera(48), 4, 50, 1, O.FLAGS_REALM)
+
+
+def test_depth_cap_and_deep_paths():
+    # a mirror box: paths bounce until the depth cap; exercises the reverse-product stack
+    walls = [S.body(R.hittable.sphere((0, 0, 0), 50.0), R.material.metal((0.99, 0.98, 0.97), 0.0)),
+             S.body(R.hittable.sphere((0, 0, -1), 0.5), R.material.dielectric(1.5)),
+             S.body(R.hittable.sphere((1.2, 0, -1), 0.5), R.material.lambertian((0.5, 0.5, 0.9)))]
+    for depth in (1, 2, 7, 50, 120):
+        assert_same(walls, CAM.i_camera(40), 4, depth, 3, O.FLAGS_MAIN)
+        assert_same(walls, CAM.i_camera(40), 4, depth, 3, O.FLAGS_REALM)
+
+
+def test_sharded_rows_union_equals_whole():
+    world, cam = S.main_hittables(), CAM.main_camera(96)
+    whole, rgb_whole, st = gpu(world, cam, 8, 50, seed=5, samples_per_unit=8)
+    for count, rows in ((2, 4), (3, 5), (8, 1), (4, 64)):
+        lin = np.zeros_like(whole)
+        rgb = np.zeros_like(rgb_whole)
+        segs = 0
+        for idx in range(count):
+            _, _, s = gpu(world, cam, 8, 50, seed=5, samples_per_unit=8, shard=(idx, count, rows),
+                          out_linear=lin, out_rgb8=rgb)
+            segs += s["segments"]
+        assert np.array_equal(lin, whole) and np.array_equal(rgb, rgb_whole) and segs == st["segments"]
+
+
+def test_chunked_units_match_oracle_and_reference_order():
+    world, cam = S.main_hittables(), CAM.main_camera(64)
+    assert_same(world, cam, 30, 50, 8, O.FLAGS_MAIN, unit=7)
+    strict, _, _ = gpu(world, cam, 30, 50, seed=8, samples_per_unit=30)
+    auto, rgb_auto, st = gpu(world, cam, 30, 50, seed=8)  # library-chosen units
+    assert st["samples_per_unit"] >= 1
+    assert np.allclose(auto, strict, rtol=1e-13, atol=1e-300)
+
+
+def test_full_size_properties_config2():
+    """BASELINE.json config 2 (1920x1080, 100 spp, depth 50) is too big for the oracle; check
+    size-independent properties: determinism, seed sensitivity, quantisation consistency,
+    a band of rows against the oracle, and the segment statistics."""
+    world, cam = S.main_hittables(), CAM.main_camera(1920)
+    assert cam.height == 1080
+    lin, rgb, st = gpu(world, cam, 100, 50, seed=1)
+    lin2, rgb2, st2 = gpu(world, cam, 100, 50, seed=1)
+    assert np.array_equal(lin, lin2) and st["segments"] == st2["segments"]
+    assert np.array_equal(render.quantise_rgb8(lin), rgb)
+    assert abs(st["segments"] / st["samples"] - 3.675) < 0.01
+    assert st["samples"] == 1920 * 1080 * 100
+    rows = (536, 540)
+    lin_o, rgb_o, _ = O.render(S.to_soa(world), cam, 100, 50, seed=1, flags=O.FLAGS_MAIN, threads=8, rows=rows,
+                               samples_per_unit=st["samples_per_unit"])
+    assert np.array_equal(lin_o[rows[0]:rows[1]], lin[rows[0]:rows[1]])
+    assert np.array_equal(rgb_o[rows[0]:rows[1]], rgb[rows[0]:rows[1]])
+
+
+def test_multi_device_equals_single_device():
+    import ctypes as C
+    n = C.c_int()
+    _abi.check(_abi.lib().rtclj_device_count(C.byref(n)))
+    if n.value < 2:
+        pytest.skip("one GPU on this box")
+    world, cam = S.cover_hittables(7), CAM.main_camera(192, 108, **S.COVER_CAMERA)
+    a, ra, sa = gpu(world, cam, 8, 50, seed=2, devices=[0])
+    b, rb, sb = gpu(world, cam, 8, 50, seed=2, devices=list(range(n.value)))
+    assert np.array_equal(a, b) and np.array_equal(ra, rb) and sa["segments"] == sb["segments"]
+
+
+def test_device_resident_context_matches_host_call():
+    import torch
+    world, cam = S.cover_hittables(7), CAM.main_camera(128, 72, **S.COVER_CAMERA)
+    ref, rgb_ref, st_ref = gpu(world, cam, 8, 50, seed=4, samples_per_unit=8)
+    ctx = render.Context(0)
+    ctx.set_scene(world)
+    out = torch.zeros((72, 128, 3), dtype=torch.float64, device="cuda:0")
+    out8 = torch.zeros((72, 128, 3), dtype=torch.uint8, device="cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.render(cam, 8, 50, seed=4, samples_per_unit=8, d_out_linear=out.data_ptr(), d_out_rgb8=out8.data_ptr(),
+               stream=stream)
+    st = ctx.stats(stream)
+    assert np.array_equal(out.cpu().numpy(), ref) and np.array_equal(out8.cpu().numpy(), rgb_ref)
+    assert st["segments"] == st_ref["segments"]
+    ctx.close()
+
+
+def test_error_behaviour():
+    import ctypes as C
+    cam = CAM.main_camera(16)
+    with pytest.raises(_abi.RtcljError) as e:
+        gpu(S.main_hittables(), cam, 0, 5)
+    assert e.value.code == _abi.E_INVALID
+    bad = S.to_soa(S.main_hittables())
+    bad[2][0] = 9
+    with pytest.raises(_abi.RtcljError):
+        gpu(bad, cam, 1, 5)
+    with pytest.raises(_abi.RtcljError) as e:
+        gpu(S.main_hittables(), cam, 1, 5, devices=[99])
+    assert e.value.code == _abi.E_INVALID
+    big = S._random_field(1, -80, 80)
+    with pytest.raises(_abi.RtcljError) as e:
+        gpu(big, cam, 1, 5)
+    assert e.value.code == _abi.E_TOO_LARGE

@@ -1,0 +1,50 @@
+"""Scratch perf probe (not the bench): device-resident renders of the cover scene."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import raytracing_clj_b200 as R
+from raytracing_clj_b200 import _abi, render
+
+
+def peaks():
+    a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int32()
+    _abi.check(_abi.lib().rtclj_calibrate_peaks(0, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+    return {"ffma_tflops": a.value, "ffma2_tflops": b.value, "dfma_tflops": c.value, "sms": n.value}
+
+
+def run(name, world, cam, spp, depth, flags, reps=3, **kw):
+    ctx = render.Context(0)
+    ctx.set_scene(world)
+    out = torch.zeros((cam.height, cam.width, 3), dtype=torch.float64, device="cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    best = None
+    for r in range(reps):
+        ctx.render(cam, spp, depth, flags=flags, d_out_linear=out.data_ptr(), stream=stream, **kw)
+        st = ctx.stats(stream)
+        if best is None or st["device_ms"] < best["device_ms"]:
+            best = st
+    n = len(world)
+    segs = best["segments"] / (best["device_ms"] * 1e-3)
+    tf = segs * (17 * n + 5) / 1e12
+    print(json.dumps({"case": name, "n": n, "ms": round(best["device_ms"], 3), "Gseg_s": round(segs / 1e9, 4),
+                      "alg_TFLOPs": round(tf, 2), "seg_per_sample": round(best["segments"] / best["samples"], 3),
+                      "exact_per_seg": round(best["exact_tests"] / max(1, best["segments"]), 2),
+                      "overflows": best["list_overflows"], "spu": best["samples_per_unit"]}), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    print(json.dumps(peaks()), flush=True)
+    S, CAM = R.scenes, R.camera
+    cover = S.cover_hittables(7)
+    run("cover_480x270x16", cover, CAM.main_camera(480, 270, **S.COVER_CAMERA), 16, 50, _abi.FLAGS_MAIN)
+    run("cover_1920x1080x16", cover, CAM.main_camera(1920, 1080, **S.COVER_CAMERA), 16, 50, _abi.FLAGS_MAIN)
+    run("default_1920x1080x16", S.main_hittables(), CAM.main_camera(1920), 16, 50, _abi.FLAGS_MAIN)
+    run("field10k_960x540x4", S.field_hittables(7), CAM.main_camera(960, 540, **S.FIELD_CAMERA), 4, 50, _abi.FLAGS_MAIN)
+    print(json.dumps(peaks()), flush=True)
