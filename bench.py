@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement (BASELINE.json): rays/sec on the RTIOW cover scene.
+
+A "ray" is one ray SEGMENT = one closest-hit search over all N spheres,
+counted by a device counter.  A "step" is one full render of the workload:
+    BASELINE.json config 3: cover scene (generator seed 7 -> 484 spheres), 1920x1080,
+    500 spp, depth 50, `main` semantics (Schlick, defocus 0.6 deg), render seed 1.
+With N GPUs the image rows are interleaved over the ranks (tiles of 4 rows, tile t ->
+rank t % N; no collective on the data path), so the total work is fixed: strong scaling.
+
+  value     whole-job segments/s with the scene resident on the device and the image left
+            in HBM (device-resident C-ABI call on torch's current stream, CUDA events,
+            per-step max over ranks)
+  e2e       the same metric through the host-buffer C-ABI call rtclj_render: scene arrays
+            copied H2D, image (linear f64 + rgb8) copied D2H into host memory every step
+  roofline  FP32 (CUDA-core) roofline of render_kernel: algorithmic flops = segments *
+            (17*N + 5) / the kernel's CUDA-event time
+  cpu_baseline  the CPU oracle (C restatement of the reference, NOT the JVM) timed on this
+            box's host cores on a bounded row sample of the same workload
+
+`--impl reference` times only the CPU restatement (the reference is Clojure; no JVM exists
+in this image, so oracle/_ref cannot be built -- see DESIGN.md).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="rtiow_cover_seed7_1920x1080_500spp_depth50", width=1920, height=1080, spp=500,
+                depth=50, scene_seed=7, render_seed=1)
+SHARD_ROWS = 4
+FLOP_PER_TEST, FLOP_PER_SEGMENT = 17, 5
+
+
+def workload_objects():
+    import raytracing_clj_b200 as R
+    world = R.scenes.cover_hittables(WORKLOAD["scene_seed"])
+    cam = R.camera.main_camera(WORKLOAD["width"], WORKLOAD["height"], **R.scenes.COVER_CAMERA)
+    return R, world, cam
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        # median over the busiest half of the samples (the sampler also sees the idle gaps)
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(world, cam, threads=None, seconds_hint=8.0):
+    """rays/s of the CPU oracle on a bounded sample: `threads` evenly spaced rows of the
+    workload at a reduced spp (the rate does not depend on spp)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import raytracing_clj_b200 as R
+    threads = threads or min(os.cpu_count() or 1, 64)
+    H = cam.height
+    step = max(1, H // threads)
+    begin = step // 2
+    nrows = len(range(begin, H, step))
+    soa = R.scenes.to_soa(world)
+    # calibrate spp for ~seconds_hint of work per thread
+    t0 = time.perf_counter()
+    _, _, st = O.render(soa, cam, 4, WORKLOAD["depth"], seed=WORKLOAD["render_seed"], flags=O.FLAGS_MAIN,
+                        threads=threads, rows=(begin, H), row_step=step, want_rgb8=False)
+    dt = time.perf_counter() - t0
+    spp = int(max(8, min(WORKLOAD["spp"], 4 * seconds_hint / max(dt, 1e-3))))
+    t0 = time.perf_counter()
+    _, _, st = O.render(soa, cam, spp, WORKLOAD["depth"], seed=WORKLOAD["render_seed"], flags=O.FLAGS_MAIN,
+                        threads=threads, rows=(begin, H), row_step=step, want_rgb8=False)
+    dt = time.perf_counter() - t0
+    sample = f"{nrows} evenly spaced rows x {cam.width} px x {spp} spp of the workload ({st.segments} segments)"
+    return st.segments / dt, min(threads, nrows), sample, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    R, world, cam = workload_objects()
+    rates, sample, cores = [], "", 0
+    for i in range(args.warmup + args.steps):
+        rate, cores, sample, dt = cpu_oracle_rate(world, cam, seconds_hint=6.0)
+        if i >= args.warmup:
+            rates.append((rate, dt))
+    value = sum(r for r, _ in rates) / len(rates)
+    line = {
+        "impl": "reference", "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(d for _, d in rates) / len(rates),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD["name"], "n_spheres": len(world), "note":
+                   "CPU restatement of the reference (oracle/rt_oracle.c); the JVM reference is not runnable here"},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spp", type=int, default=None, help="override the workload's spp (invalid as a bench value)")
+    args = ap.parse_args()
+    if args.spp:
+        WORKLOAD["spp"] = args.spp
+        WORKLOAD["name"] += f"_OVERRIDE_spp{args.spp}"
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from raytracing_clj_b200 import _abi, render
+    R, world, cam = workload_objects()
+    n = len(world)
+    W, H, spp, depth = cam.width, cam.height, WORKLOAD["spp"], WORKLOAD["depth"]
+    shard = (rank, world_size, SHARD_ROWS) if world_size > 1 else None
+    flags = _abi.FLAGS_MAIN
+
+    # arithmetic peaks of this GPU (pure-FMA kernels), before the timed region
+    pk = [C.c_double(), C.c_double(), C.c_double()]
+    sms = C.c_int32()
+    _abi.check(_abi.lib().rtclj_calibrate_peaks(local_rank, C.byref(pk[0]), C.byref(pk[1]), C.byref(pk[2]), C.byref(sms)))
+
+    ctx = render.Context(local_rank)
+    ctx.set_scene(world)
+    out_lin = torch.zeros((H, W, 3), dtype=torch.float64, device=dev)
+    out_rgb = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ctx.render(cam, spp, depth, seed=WORKLOAD["render_seed"], flags=flags, shard=shard,
+                   d_out_linear=out_lin.data_ptr(), d_out_rgb8=out_rgb.data_ptr(), stream=stream)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms, seg_local = [], 0
+    barrier()
+    for s0, s1 in evs:
+        flush.zero_()  # L2 flush between timed iterations (not timed)
+        s0.record()
+        step()
+        s1.record()
+        st = ctx.stats(stream)  # synchronises the stream; reads the device counters
+        kernel_ms.append(st["kernel_ms"])
+        seg_local = st["segments"]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in evs], dtype=torch.float64, device=dev)
+    segs = torch.tensor([float(seg_local)], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # per step, the slowest rank
+        dist.all_reduce(segs, op=dist.ReduceOp.SUM)
+    total_ms = float(step_ms.sum().item())
+    segs_per_step = float(segs.item())
+    value = segs_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through rtclj_render, H2D + D2H inside the timed region
+    soa = R.scenes.to_soa(world)
+    shm_path = f"/dev/shm/rtclj_bench_{os.environ.get('MASTER_PORT', 'single')}"
+    lin_bytes, rgb_bytes = H * W * 3 * 8, H * W * 3
+    if rank == 0:
+        with open(shm_path, "wb") as f:
+            f.truncate(lin_bytes + rgb_bytes)
+    barrier()
+    host_lin = np.memmap(shm_path, dtype=np.float64, mode="r+", offset=0, shape=(H, W, 3))
+    host_rgb = np.memmap(shm_path, dtype=np.uint8, mode="r+", offset=lin_bytes, shape=(H, W, 3))
+
+    def e2e_step():
+        return render.render(soa, cam, spp, depth, seed=WORKLOAD["render_seed"], flags=flags, shard=shard,
+                             devices=[local_rank], out_linear=host_lin, out_rgb8=host_rgb)[2]
+
+    e2e_step()
+    e2e_times = []
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        barrier()
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_t = torch.tensor(e2e_times, dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = segs_per_step * e2e_steps / float(e2e_t.sum().item())
+    checksum = int(np.asarray(host_rgb[::97, ::89]).sum()) if rank == 0 else 0
+    h2d = sum(a.nbytes for a in soa) * world_size
+    barrier()
+    if rank == 0:
+        try:
+            os.unlink(shm_path)
+        except OSError:
+            pass
+
+    if rank != 0:
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    sm_max = float(peaks.get("sm_max_mhz") or 1965.0)
+    peak_nominal = sms.value * 128 * 2 * sm_max * 1e6 / 1e12
+    k_ms = sum(kernel_ms) / len(kernel_ms)
+    achieved = seg_local * (FLOP_PER_TEST * n + FLOP_PER_SEGMENT) / (k_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s", "frac": achieved / peak_nominal,
+        "traffic": None, "kernel": "render_kernel", "kernel_ms": k_ms,
+        "peak_source": f"{sms.value} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json"
+                       f"{'' if peaks else ' MISSING: fallback 1965'}); the path is CUDA-core fp32, not HBM or tensor",
+        "peak_calibrated": {"ffma": pk[0].value, "ffma2": pk[1].value, "dfma_fp64": pk[2].value, "unit": "TFLOP/s"},
+        "frac_of_calibrated_ffma2": achieved / pk[1].value if pk[1].value else None,
+        "algorithmic_flops": f"segments x ({FLOP_PER_TEST}*N + {FLOP_PER_SEGMENT}), N={n}",
+    }
+    cpu = None
+    if world_size == 1 and not args.no_cpu_baseline:
+        rate, cores, sample, _ = cpu_oracle_rate(world, cam)
+        cpu = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+    line = {
+        "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world_size, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 cull + f64 exact hit/shade", "data": "synthetic",
+        "config": {"workload": WORKLOAD["name"], "n_spheres": n, "samples_per_step": W * H * spp,
+                   "segments_per_step": segs_per_step, "samples_per_sec": W * H * spp * args.steps / (total_ms * 1e-3),
+                   "parallelism": f"rows interleaved over {world_size} GPU(s), tiles of {SHARD_ROWS} rows",
+                   "l2": "flushed between timed steps (256 MiB write); the scene lives in shared memory",
+                   "rgb8_checksum": checksum},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": lin_bytes + rgb_bytes, "ms_per_step": 1e3 * float(e2e_t.sum().item()) / e2e_steps},
+        "gpu_launches": 2 * args.steps * world_size,  # render_kernel + finalize_kernel per step per rank
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

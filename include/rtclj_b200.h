@@ -133,7 +133,8 @@ typedef struct rtclj_stats {
                                BASELINE.json's metric), counted on the device      */
   uint64_t exact_tests;     /* fp64 ray-sphere tests run on cull survivors          */
   uint64_t list_overflows;  /* segments whose survivor list overflowed (full fp64 scan) */
-  double device_ms;         /* CUDA-event time of the render kernels                */
+  double device_ms;         /* CUDA-event time of render + finalize kernels         */
+  double kernel_ms;         /* CUDA-event time of the render kernel alone           */
   double total_ms;          /* wall time of the call, including copies              */
   int32_t samples_per_unit; /* the unit size actually used                          */
   int32_t n_devices;

@@ -315,7 +315,7 @@ int rto_quantise(double c, int linear) {
   return (v != v) ? 0 : (int)v;
 }
 
-static void render_rows(tracer *tr, int row_begin, int row_end, double *out_linear,
+static void render_rows(tracer *tr, int row_begin, int row_end, int row_step, double *out_linear,
                         uint8_t *out_rgb8) {
   const rto_camera *cam = tr->cam;
   const rto_params *prm = tr->prm;
@@ -323,7 +323,7 @@ static void render_rows(tracer *tr, int row_begin, int row_end, double *out_line
   int unit = prm->samples_per_unit;
   if (unit <= 0 || unit > spp) unit = spp;
   const double scale = 1.0 / (double)spp; /* realm/raytracing.clj:25 */
-  for (int j = row_begin; j < row_end; ++j) {
+  for (int j = row_begin; j < row_end; j += row_step) {
     for (int i = 0; i < W; ++i) {
       uint32_t pixel = (uint32_t)j * (uint32_t)W + (uint32_t)i;
       v3 acc = v3_make(0.0, 0.0, 0.0);
@@ -348,26 +348,34 @@ static void render_rows(tracer *tr, int row_begin, int row_end, double *out_line
 
 typedef struct {
   tracer tr;
-  int row_begin, row_end;
+  int row_begin, row_end, row_step;
   double *out_linear;
   uint8_t *out_rgb8;
 } job;
 
 static void *job_main(void *p) {
   job *jb = (job *)p;
-  render_rows(&jb->tr, jb->row_begin, jb->row_end, jb->out_linear, jb->out_rgb8);
+  render_rows(&jb->tr, jb->row_begin, jb->row_end, jb->row_step, jb->out_linear, jb->out_rgb8);
   return NULL;
 }
 
 int rto_render(const rto_scene *scene, const rto_camera *cam, const rto_params *prm,
                int threads, int row_begin, int row_end, double *out_linear,
                uint8_t *out_rgb8, rto_stats *stats) {
+  return rto_render_strided(scene, cam, prm, threads, row_begin, row_end, 1, out_linear, out_rgb8,
+                            stats);
+}
+
+int rto_render_strided(const rto_scene *scene, const rto_camera *cam, const rto_params *prm,
+                       int threads, int row_begin, int row_end, int row_step, double *out_linear,
+                       uint8_t *out_rgb8, rto_stats *stats) {
   if (!scene || !cam || !prm || scene->n < 0 || cam->width <= 0 || cam->height <= 0 ||
       prm->spp <= 0)
     return 1;
   if (row_begin < 0) row_begin = 0;
   if (row_end > cam->height) row_end = cam->height;
-  int rows = row_end - row_begin;
+  if (row_step < 1) row_step = 1;
+  int rows = row_end > row_begin ? (row_end - row_begin + row_step - 1) / row_step : 0;
   if (rows <= 0) return 0;
   if (threads < 1) threads = 1;
   if (threads > rows) threads = rows;
@@ -377,13 +385,14 @@ int rto_render(const rto_scene *scene, const rto_camera *cam, const rto_params *
   int depth_cap = prm->max_depth > 0 ? prm->max_depth : 1;
   int njobs = 0;
   for (int t = 0; t < threads; ++t) {
-    int b = row_begin + t * chunk, e = b + chunk < row_end ? b + chunk : row_end;
+    int b = row_begin + t * chunk * row_step;
+    int e = b + chunk * row_step < row_end ? b + chunk * row_step : row_end;
     if (b >= e) break;
     job *jb = &jobs[njobs++];
     jb->tr.scene = scene; jb->tr.cam = cam; jb->tr.prm = prm;
     jb->tr.k0 = (uint32_t)prm->seed; jb->tr.k1 = (uint32_t)(prm->seed >> 32);
     jb->tr.att_stack = (int32_t *)malloc(sizeof(int32_t) * (size_t)depth_cap);
-    jb->row_begin = b; jb->row_end = e;
+    jb->row_begin = b; jb->row_end = e; jb->row_step = row_step;
     jb->out_linear = out_linear; jb->out_rgb8 = out_rgb8;
   }
   if (njobs == 1) job_main(&jobs[0]);

@@ -93,6 +93,13 @@ int rto_render(const rto_scene *scene, const rto_camera *cam, const rto_params *
                int threads, int row_begin, int row_end, double *out_linear,
                uint8_t *out_rgb8, rto_stats *stats);
 
+/* Same, over rows row_begin, row_begin+row_step, ... < row_end (a bounded, evenly spread
+ * sample of a big image for the CPU-baseline timing).  The row list is cut into
+ * contiguous chunks of ceil(count/threads) rows, one per thread. */
+int rto_render_strided(const rto_scene *scene, const rto_camera *cam, const rto_params *prm,
+                       int threads, int row_begin, int row_end, int row_step, double *out_linear,
+                       uint8_t *out_rgb8, rto_stats *stats);
+
 /* Single closest-hit query (hit-anything) for unit tests: returns index or -1. */
 int rto_hit_anything(const rto_scene *scene, const double origin[3], const double dir[3],
                      double t_min, double t_max, double *t_out, double point[3],

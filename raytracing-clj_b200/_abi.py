@@ -39,7 +39,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("segments", C.c_uint64), ("exact_tests", C.c_uint64),
-                ("list_overflows", C.c_uint64), ("device_ms", C.c_double), ("total_ms", C.c_double),
+                ("list_overflows", C.c_uint64), ("device_ms", C.c_double), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
                 ("samples_per_unit", C.c_int32), ("n_devices", C.c_int32)]
 
     def as_dict(self):

@@ -76,7 +76,7 @@ struct rtclj_ctx {
   DevBuf<unsigned short> stack;
   DevBuf<double> out_linear;            // used by the host-buffer entry points
   DevBuf<unsigned char> out_rgb8;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   cudaStream_t own_stream = nullptr;
   int last_spu = 0;
   bool have_scene = false;
@@ -191,6 +191,7 @@ int rtclj_ctx_create(int32_t device, rtclj_ctx** out) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreate(&c->ev2));
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CU(c->counters.reserve(8));
   CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
@@ -205,6 +206,7 @@ void rtclj_ctx_destroy(rtclj_ctx* c) {
   c->counters.release(); c->stack.release(); c->out_linear.release(); c->out_rgb8.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev2) cudaEventDestroy(c->ev2);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -332,6 +334,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     render_kernel<<<grid, kThreads, smem, stream>>>(P);
     CU(cudaGetLastError());
   }
+  CU(cudaEventRecord(c->ev1, stream));
   FParams F;
   F.partial = c->partial.p; F.out_linear = (double*)d_out_linear; F.out_rgb8 = (unsigned char*)d_out_rgb8;
   F.W = W; F.spp = prm->spp; F.nchunks = nchunks;
@@ -342,7 +345,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     finalize_kernel<<<blocks, 256, 0, stream>>>(F);
     CU(cudaGetLastError());
   }
-  CU(cudaEventRecord(c->ev1, stream));
+  CU(cudaEventRecord(c->ev2, stream));
   return RTCLJ_OK;
 }
 
@@ -355,7 +358,8 @@ int rtclj_ctx_stats(rtclj_ctx* c, void* stream_, rtclj_stats* st) {
   std::memset(st, 0, sizeof *st);
   st->samples = h[1]; st->segments = h[2]; st->exact_tests = h[3]; st->list_overflows = h[4];
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) st->device_ms = ms; else cudaGetLastError();
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev2) == cudaSuccess) st->device_ms = ms; else cudaGetLastError();
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) st->kernel_ms = ms; else cudaGetLastError();
   st->samples_per_unit = c->last_spu;
   st->n_devices = 1;
   return RTCLJ_OK;
@@ -443,6 +447,7 @@ int rtclj_render_multi(const rtclj_scene* scene, const rtclj_camera* cam, const 
     total.samples += s.samples; total.segments += s.segments; total.exact_tests += s.exact_tests;
     total.list_overflows += s.list_overflows;
     total.device_ms = std::max(total.device_ms, s.device_ms);
+    total.kernel_ms = std::max(total.kernel_ms, s.kernel_ms);
     total.samples_per_unit = s.samples_per_unit;
   }
   total.n_devices = n_devices;

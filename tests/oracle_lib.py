@@ -60,6 +60,9 @@ def lib():
         _lib.rto_render.restype = C.c_int
         _lib.rto_render.argtypes = [C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Params), C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        _lib.rto_render_strided.restype = C.c_int
+        _lib.rto_render_strided.argtypes = [C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Params), C.c_int,
+                                            C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
         _lib.rto_uniform.restype = C.c_double
         _lib.rto_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
         _lib.rto_philox4x32_10.restype = None
@@ -98,7 +101,7 @@ def make_camera(cam) -> Camera:
 
 
 def render(soa, cam, spp, max_depth, seed=1, flags=FLAGS_MAIN, threads=1, rows=None,
-           samples_per_unit=0, want_rgb8=True):
+           samples_per_unit=0, want_rgb8=True, row_step=1):
     """Returns (linear float64 [H,W,3], rgb8 uint8 [H,W,3] or None, Stats)."""
     sc, cm = make_scene(soa), make_camera(cam)
     prm = Params(int(spp), int(max_depth), int(seed), int(flags), int(samples_per_unit))
@@ -107,8 +110,9 @@ def render(soa, cam, spp, max_depth, seed=1, flags=FLAGS_MAIN, threads=1, rows=N
     rgb = np.zeros((H, W, 3), dtype=np.uint8) if want_rgb8 else None
     st = Stats()
     r0, r1 = (0, H) if rows is None else rows
-    rc = lib().rto_render(C.byref(sc), C.byref(cm), C.byref(prm), int(threads), int(r0), int(r1),
-                          lin.ctypes.data, rgb.ctypes.data if want_rgb8 else None, C.byref(st))
+    rc = lib().rto_render_strided(C.byref(sc), C.byref(cm), C.byref(prm), int(threads), int(r0), int(r1),
+                                  int(row_step), lin.ctypes.data, rgb.ctypes.data if want_rgb8 else None,
+                                  C.byref(st))
     if rc != 0:
         raise RuntimeError(f"rto_render failed: {rc}")
     return lin, rgb, st
