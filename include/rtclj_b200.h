@@ -133,6 +133,7 @@ typedef struct rtclj_stats {
                                BASELINE.json's metric), counted on the device      */
   uint64_t exact_tests;     /* fp64 ray-sphere tests run on cull survivors          */
   uint64_t list_overflows;  /* segments whose survivor list overflowed (full fp64 scan) */
+  uint64_t prefilter_tests; /* cull survivors examined by the fp32 root prefilter          */
   double device_ms;         /* CUDA-event time of render + finalize kernels         */
   double kernel_ms;         /* CUDA-event time of the render kernel alone           */
   double total_ms;          /* wall time of the call, including copies              */

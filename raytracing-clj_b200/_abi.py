@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librtclj_b200.so")
+LIB_PATH = os.environ.get("RTCLJ_LIB") or os.path.join(HERE, "librtclj_b200.so")  # RTCLJ_LIB: tuning experiments only
 
 LAMBERTIAN, METAL, DIELECTRIC = 0, 1, 2
 F_NEAR_ZERO_GUARD, F_SCHLICK, F_REVERSE_PRODUCT, F_MEAN_DIVIDE = 1, 2, 4, 8
@@ -39,7 +39,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("segments", C.c_uint64), ("exact_tests", C.c_uint64),
-                ("list_overflows", C.c_uint64), ("device_ms", C.c_double), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
+                ("list_overflows", C.c_uint64), ("prefilter_tests", C.c_uint64), ("device_ms", C.c_double), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
                 ("samples_per_unit", C.c_int32), ("n_devices", C.c_int32)]
 
     def as_dict(self):

@@ -66,7 +66,7 @@ struct rtclj_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  int n = 0, nquads = 0;
+  int n = 0, nblocks = 0;
   double shift[3] = {0, 0, 0};
   DevBuf<float4> geom32;
   DevBuf<Geom64> geom64;
@@ -84,8 +84,8 @@ struct rtclj_ctx {
 
 namespace {
 
-size_t smem_needed(int nquads) {
-  return (size_t)nquads * 64 + (size_t)kListCap * kThreads * 2 + 16;
+size_t smem_needed(int nblocks) {
+  return (size_t)nblocks * kBlockPairs * 32 + (size_t)kListCap * kThreads * 2 + 16;
 }
 
 int local_rows_of(int H, int shard_index, int shard_count, int shard_rows) {
@@ -218,10 +218,12 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
   if (n > 0 && (!s->center_xyz || !s->radius || !s->material || !s->albedo_rgb || !s->fuzz || !s->ior))
     return fail(RTCLJ_E_INVALID, "null scene array");
   if (n > 65532) return fail(RTCLJ_E_TOO_LARGE, "%d spheres: survivor lists hold 16-bit indices", n);
-  const int nquads = (n + 3) / 4;
-  if (smem_needed(nquads) > c->smem_optin)
+  const int per_block = 2 * kBlockPairs;
+  const int nblocks = (n + per_block - 1) / per_block;
+  const int npad = nblocks * per_block;
+  if (smem_needed(nblocks) > c->smem_optin)
     return fail(RTCLJ_E_TOO_LARGE, "%d spheres need %zu B of shared memory, device offers %zu", n,
-                smem_needed(nquads), c->smem_optin);
+                smem_needed(nblocks), c->smem_optin);
   for (int i = 0; i < n; ++i) {
     const int k = s->material[i];
     if (k != RTCLJ_LAMBERTIAN && k != RTCLJ_METAL && k != RTCLJ_DIELECTRIC)
@@ -242,8 +244,8 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
   }
   std::vector<Geom64> g64((size_t)std::max(n, 1));
   std::vector<MatRec> mats((size_t)std::max(n, 1));
-  std::vector<float> g32((size_t)std::max(nquads, 1) * 16);
-  for (int i = 0; i < nquads * 4; ++i) {
+  std::vector<float> g32((size_t)std::max(npad, 2) * 4);
+  for (int i = 0; i < npad; ++i) {
     float cx = 0.f, cy = 0.f, cz = 0.f, r2s = -1e30f;  // padding never survives the cull
     if (i < n) {
       const double* C = s->center_xyz + 3 * i;
@@ -253,6 +255,14 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
       m.albedo[0] = s->albedo_rgb[3 * i]; m.albedo[1] = s->albedo_rgb[3 * i + 1]; m.albedo[2] = s->albedo_rgb[3 * i + 2];
       m.kind = s->material[i];
       m.param = m.kind == RTCLJ_METAL ? s->fuzz[i] : s->ior[i];
+      if (m.kind == RTCLJ_DIELECTRIC) {
+        // material.clj:37 (/ 1.0 refraction-index) and material.clj:31 (/ (- 1.0 ri) (+ 1.0 ri)),
+        // the same IEEE double operations the reference performs per hit, done once here
+        const double ior = s->ior[i], inv = 1.0 / ior;
+        m.albedo[0] = inv;
+        m.albedo[1] = (1.0 - inv) / (1.0 + inv);
+        m.albedo[2] = (1.0 - ior) / (1.0 + ior);
+      }
       m.pad = 0;
       mats[(size_t)i] = m;
       cx = (float)(C[0] - shift[0]); cy = (float)(C[1] - shift[1]); cz = (float)(C[2] - shift[2]);
@@ -267,13 +277,13 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
   }
   CU(c->geom64.reserve((size_t)std::max(n, 1)));
   CU(c->mat.reserve((size_t)std::max(n, 1)));
-  CU(c->geom32.reserve((size_t)std::max(nquads, 1) * 4));
+  CU(c->geom32.reserve((size_t)std::max(npad, 2)));
   if (n > 0) {
     CU(cudaMemcpy(c->geom64.p, g64.data(), sizeof(Geom64) * (size_t)n, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->mat.p, mats.data(), sizeof(MatRec) * (size_t)n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->geom32.p, g32.data(), sizeof(float) * 16 * (size_t)nquads, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->geom32.p, g32.data(), sizeof(float) * 4 * (size_t)npad, cudaMemcpyHostToDevice));
   }
-  c->n = n; c->nquads = nquads;
+  c->n = n; c->nblocks = nblocks;
   std::memcpy(c->shift, shift, sizeof shift);
   c->have_scene = true;
   return RTCLJ_OK;
@@ -320,7 +330,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.use_defocus = !(cam->defocus_angle <= 0.0);
     P.W = W; P.H = H; P.spp = prm->spp; P.max_depth = prm->max_depth;
     P.flags = prm->flags; P.k0 = (unsigned)prm->seed; P.k1 = (unsigned)(prm->seed >> 32);
-    P.n = c->n; P.nquads = c->nquads; P.geom_bytes = (unsigned)c->nquads * 64u;
+    P.n = c->n; P.nblocks = c->nblocks; P.geom_bytes = (unsigned)c->nblocks * kBlockPairs * 32u;
     P.shard_index = shard_index; P.shard_count = shard_count; P.shard_rows = shard_rows;
     P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
     P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
@@ -330,7 +340,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
       CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
       P.stack = c->stack.p;
     }
-    const size_t smem = smem_needed(c->nquads);
+    const size_t smem = smem_needed(c->nblocks);
     render_kernel<<<grid, kThreads, smem, stream>>>(P);
     CU(cudaGetLastError());
   }
@@ -357,6 +367,7 @@ int rtclj_ctx_stats(rtclj_ctx* c, void* stream_, rtclj_stats* st) {
   CU(cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
   std::memset(st, 0, sizeof *st);
   st->samples = h[1]; st->segments = h[2]; st->exact_tests = h[3]; st->list_overflows = h[4];
+  st->prefilter_tests = h[5];
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, c->ev0, c->ev2) == cudaSuccess) st->device_ms = ms; else cudaGetLastError();
   if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) st->kernel_ms = ms; else cudaGetLastError();
@@ -445,7 +456,7 @@ int rtclj_render_multi(const rtclj_scene* scene, const rtclj_camera* cam, const 
     rc = rtclj_ctx_stats(ctxs[(size_t)d], ctxs[(size_t)d]->own_stream, &s);
     if (rc) return rc;
     total.samples += s.samples; total.segments += s.segments; total.exact_tests += s.exact_tests;
-    total.list_overflows += s.list_overflows;
+    total.list_overflows += s.list_overflows; total.prefilter_tests += s.prefilter_tests;
     total.device_ms = std::max(total.device_ms, s.device_ms);
     total.kernel_ms = std::max(total.kernel_ms, s.kernel_ms);
     total.samples_per_unit = s.samples_per_unit;

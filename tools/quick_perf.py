@@ -34,17 +34,26 @@ def run(name, world, cam, spp, depth, flags, reps=3, **kw):
     tf = segs * (17 * n + 5) / 1e12
     print(json.dumps({"case": name, "n": n, "ms": round(best["device_ms"], 3), "Gseg_s": round(segs / 1e9, 4),
                       "alg_TFLOPs": round(tf, 2), "seg_per_sample": round(best["segments"] / best["samples"], 3),
-                      "exact_per_seg": round(best["exact_tests"] / max(1, best["segments"]), 2),
+                      "exact_per_seg": round(best["exact_tests"] / max(1, best["segments"]), 2), "pref_per_seg": round(best["prefilter_tests"] / max(1, best["segments"]), 2),
                       "overflows": best["list_overflows"], "spu": best["samples_per_unit"]}), flush=True)
     ctx.close()
 
 
 if __name__ == "__main__":
-    print(json.dumps(peaks()), flush=True)
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     S, CAM = R.scenes, R.camera
     cover = S.cover_hittables(7)
-    run("cover_480x270x16", cover, CAM.main_camera(480, 270, **S.COVER_CAMERA), 16, 50, _abi.FLAGS_MAIN)
-    run("cover_1920x1080x16", cover, CAM.main_camera(1920, 1080, **S.COVER_CAMERA), 16, 50, _abi.FLAGS_MAIN)
-    run("default_1920x1080x16", S.main_hittables(), CAM.main_camera(1920), 16, 50, _abi.FLAGS_MAIN)
-    run("field10k_960x540x4", S.field_hittables(7), CAM.main_camera(960, 540, **S.FIELD_CAMERA), 4, 50, _abi.FLAGS_MAIN)
-    print(json.dumps(peaks()), flush=True)
+    cases = {
+        "cover_480x270x16": lambda: (cover, CAM.main_camera(480, 270, **S.COVER_CAMERA), 16),
+        "cover_1920x1080x16": lambda: (cover, CAM.main_camera(1920, 1080, **S.COVER_CAMERA), 16),
+        "default_1920x1080x16": lambda: (S.main_hittables(), CAM.main_camera(1920), 16),
+        "field10k_960x540x4": lambda: (S.field_hittables(7), CAM.main_camera(960, 540, **S.FIELD_CAMERA), 4),
+    }
+    if not only:
+        print(json.dumps(peaks()), flush=True)
+    for name, mk in cases.items():
+        if only and name != only:
+            continue
+        world, cam, spp = mk()
+        run(name, world, cam, spp, 50, _abi.FLAGS_MAIN, reps=reps)
