@@ -66,7 +66,7 @@ struct rtclj_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  int n = 0, nblocks = 0;
+  int n = 0, nhalf = 0;  // spheres; 16-sphere half blocks of the padded cull table
   double shift[3] = {0, 0, 0};
   DevBuf<float4> geom32;
   DevBuf<Geom64> geom64;
@@ -84,8 +84,8 @@ struct rtclj_ctx {
 
 namespace {
 
-size_t smem_needed(int nblocks) {
-  return (size_t)nblocks * kBlockPairs * 32 + (size_t)kListCap * kThreads * 2 + 16;
+size_t smem_needed(int nhalf) {
+  return (size_t)nhalf * 256 + (size_t)kListCap * kThreads * 4 + 16;
 }
 
 int local_rows_of(int H, int shard_index, int shard_count, int shard_rows) {
@@ -218,12 +218,11 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
   if (n > 0 && (!s->center_xyz || !s->radius || !s->material || !s->albedo_rgb || !s->fuzz || !s->ior))
     return fail(RTCLJ_E_INVALID, "null scene array");
   if (n > 65532) return fail(RTCLJ_E_TOO_LARGE, "%d spheres: survivor lists hold 16-bit indices", n);
-  const int per_block = 2 * kBlockPairs;
-  const int nblocks = (n + per_block - 1) / per_block;
-  const int npad = nblocks * per_block;
-  if (smem_needed(nblocks) > c->smem_optin)
+  const int nhalf = (n + 15) / 16;  // the cull table is padded to 16-sphere half blocks
+  const int npad = nhalf * 16;
+  if (smem_needed(nhalf) > c->smem_optin)
     return fail(RTCLJ_E_TOO_LARGE, "%d spheres need %zu B of shared memory, device offers %zu", n,
-                smem_needed(nblocks), c->smem_optin);
+                smem_needed(nhalf), c->smem_optin);
   for (int i = 0; i < n; ++i) {
     const int k = s->material[i];
     if (k != RTCLJ_LAMBERTIAN && k != RTCLJ_METAL && k != RTCLJ_DIELECTRIC)
@@ -266,9 +265,10 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
       m.pad = 0;
       mats[(size_t)i] = m;
       cx = (float)(C[0] - shift[0]); cy = (float)(C[1] - shift[1]); cz = (float)(C[2] - shift[2]);
-      const double mc = std::max(std::fabs((double)cx), std::max(std::fabs((double)cy), std::fabs((double)cz)));
+      // Ws = r^2 (1 + 8 eps) - |c|^2 (1 - 96 eps), c = the fp32-rounded shifted centre; rounded UP
       const double eps = (double)kEps32;
-      r2s = round_up_to_float(r * r * (1.0 + 8.0 * eps) + 32.0 * eps * mc * mc);
+      const double c2 = (double)cx * cx + (double)cy * cy + (double)cz * cz;
+      r2s = round_up_to_float(r * r * (1.0 + 8.0 * eps) - c2 * (1.0 - 96.0 * eps));
     }
     // pair-packed: pair p = i/2, half h = i&1 -> {cx[h], cy[2+h]} in vec0, {cz[h], r2s[2+h]} in vec1
     const int p = i >> 1, h = i & 1;
@@ -283,7 +283,7 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
     CU(cudaMemcpy(c->mat.p, mats.data(), sizeof(MatRec) * (size_t)n, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->geom32.p, g32.data(), sizeof(float) * 4 * (size_t)npad, cudaMemcpyHostToDevice));
   }
-  c->n = n; c->nblocks = nblocks;
+  c->n = n; c->nhalf = nhalf;
   std::memcpy(c->shift, shift, sizeof shift);
   c->have_scene = true;
   return RTCLJ_OK;
@@ -330,7 +330,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.use_defocus = !(cam->defocus_angle <= 0.0);
     P.W = W; P.H = H; P.spp = prm->spp; P.max_depth = prm->max_depth;
     P.flags = prm->flags; P.k0 = (unsigned)prm->seed; P.k1 = (unsigned)(prm->seed >> 32);
-    P.n = c->n; P.nblocks = c->nblocks; P.geom_bytes = (unsigned)c->nblocks * kBlockPairs * 32u;
+    P.n = c->n; P.nblocks = c->nhalf / 2; P.tail8 = c->nhalf & 1; P.geom_bytes = (unsigned)c->nhalf * 256u;
     P.shard_index = shard_index; P.shard_count = shard_count; P.shard_rows = shard_rows;
     P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
     P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
@@ -340,7 +340,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
       CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
       P.stack = c->stack.p;
     }
-    const size_t smem = smem_needed(c->nblocks);
+    const size_t smem = smem_needed(c->nhalf);
     render_kernel<<<grid, kThreads, smem, stream>>>(P);
     CU(cudaGetLastError());
   }

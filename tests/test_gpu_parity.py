@@ -80,7 +80,8 @@ def test_cover_scene_bit_exact():
     world = S.cover_hittables(7)
     assert 480 <= len(world) <= 488
     st = assert_same(world, CAM.main_camera(160, 90, **S.COVER_CAMERA), 8, 50, 7, O.FLAGS_MAIN)
-    assert st["list_overflows"] == 0
+    # list flushes (a ray whose survivors span more than 16 half blocks) must stay rare
+    assert st["list_overflows"] < 1e-4 * st["segments"]
     # the cull must leave only a handful of fp64 tests per segment
     assert st["exact_tests"] / st["segments"] < 12
 

@@ -47,6 +47,7 @@ if __name__ == "__main__":
     cases = {
         "cover_480x270x16": lambda: (cover, CAM.main_camera(480, 270, **S.COVER_CAMERA), 16),
         "cover_1920x1080x16": lambda: (cover, CAM.main_camera(1920, 1080, **S.COVER_CAMERA), 16),
+        "cover_normalshade_1920x1080x32": lambda: (cover, CAM.main_camera(1920, 1080, **S.COVER_CAMERA), 32, _abi.FLAGS_I),
         "default_1920x1080x16": lambda: (S.main_hittables(), CAM.main_camera(1920), 16),
         "field10k_960x540x4": lambda: (S.field_hittables(7), CAM.main_camera(960, 540, **S.FIELD_CAMERA), 4),
     }
@@ -55,5 +56,5 @@ if __name__ == "__main__":
     for name, mk in cases.items():
         if only and name != only:
             continue
-        world, cam, spp = mk()
-        run(name, world, cam, spp, 50, _abi.FLAGS_MAIN, reps=reps)
+        world, cam, spp, *fl = mk()
+        run(name, world, cam, spp, 50, fl[0] if fl else _abi.FLAGS_MAIN, reps=reps)
