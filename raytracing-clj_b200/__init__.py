@@ -9,4 +9,11 @@ Host-side modules mirror the reference's namespaces for this path:
 There is no CPU fallback: render.* raises if the CUDA library or a GPU is missing."""
 from . import camera, hittable, material, scenes  # noqa: F401
 
-__all__ = ["camera", "hittable", "material", "scenes"]
+__all__ = ["camera", "hittable", "material", "scenes", "render", "main"]
+
+
+def __getattr__(name):  # render / main load the CUDA library lazily (and loudly)
+    if name in ("render", "main", "_abi"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

@@ -15,6 +15,18 @@ from . import _abi, scenes
 from .camera import Camera
 
 
+def shard_rows(height: int, index: int, count: int, rows: int) -> List[int]:
+    """The image rows shard `index` of `count` owns: rows are cut into tiles of `rows` rows and
+    tile t belongs to shard t % count (rtclj_params.shard_*)."""
+    if count <= 1:
+        return list(range(height))
+    out: List[int] = []
+    ntiles = (height + rows - 1) // rows
+    for t in range(index, ntiles, count):
+        out.extend(range(t * rows, min(height, (t + 1) * rows)))
+    return out
+
+
 def _scene_struct(soa):
     center, radius, kind, albedo, fuzz, ior = soa
     s = _abi.Scene(len(radius), 0, center.ctypes.data, radius.ctypes.data, kind.ctypes.data,
