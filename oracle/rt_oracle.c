@@ -11,9 +11,11 @@
  * so that the CUDA path can be compared draw for draw:
  *   stage 0   = camera ray: block 0 = (jitter-x, jitter-y, disk0.x, disk0.y),
  *               block n>=1 = disk candidates 2n-1 (words 0,1) and 2n (words 2,3)
- *   stage s>0 = scatter at the s-th hit of the path: unit-vector candidate n uses
- *               words 0,1,2 of block n; the Schlick draw is word 0 of block 0.
- * uniform = (word >> 8) * 2^-24  (SURVEY.md 8d / Appendix E).
+ *   stage s>0 = scatter at the s-th hit of the path: block n carries unit-vector
+ *               candidates 2n (words 0,1) and 2n+1 (words 2,3); a candidate's x, y, z
+ *               are the three 21-bit fields of its 64 bits (lo word first), each
+ *               mapped to -1 + 2 * field * 2^-21; the Schlick draw is word 0 of block 0.
+ * uniform = (word >> 8) * 2^-24 everywhere else.
  */
 #include "rt_oracle.h"
 
@@ -87,10 +89,15 @@ typedef struct {
   uint32_t pixel, sample, stage;
 } rng_key;
 
-static inline void draw_block(tracer *tr, rng_key k, uint32_t block, double u[4]) {
-  uint32_t ctr[4] = {k.pixel, k.sample, k.stage, block}, out[4];
+static inline void draw_words(tracer *tr, rng_key k, uint32_t block, uint32_t out[4]) {
+  uint32_t ctr[4] = {k.pixel, k.sample, k.stage, block};
   rto_philox4x32_10(ctr, tr->k0, tr->k1, out);
   tr->st.rng_blocks++;
+}
+
+static inline void draw_block(tracer *tr, rng_key k, uint32_t block, double u[4]) {
+  uint32_t out[4];
+  draw_words(tr, k, block, out);
   for (int w = 0; w < 4; ++w) u[w] = word_to_uniform(out[w]);
 }
 
@@ -100,11 +107,16 @@ static inline double sym(double u) { return -1.0 + 2.0 * u; }
 /* vec3a/random-unit-vec3 (vec3a.clj:74-79), Realm.randUnitVec3 (realm/vec3.clj:113-121) */
 static v3 random_unit(tracer *tr, rng_key k) {
   for (uint32_t block = 0;; ++block) {
-    double u[4];
-    draw_block(tr, k, block, u);
-    double x = sym(u[0]), y = sym(u[1]), z = sym(u[2]);
-    double lensq = x * x + y * y + z * z;
-    if (lensq > 1e-160 && lensq <= 1.0) return v3_divs(v3_make(x, y, z), sqrt(lensq));
+    uint32_t w[4];
+    draw_words(tr, k, block, w);
+    for (int half = 0; half < 2; ++half) { /* two candidates per block, 3 x 21 bits each */
+      uint64_t bits = (uint64_t)w[2 * half] | ((uint64_t)w[2 * half + 1] << 32);
+      double x = sym((double)(bits & 0x1FFFFFu) * (1.0 / 2097152.0));
+      double y = sym((double)((bits >> 21) & 0x1FFFFFu) * (1.0 / 2097152.0));
+      double z = sym((double)((bits >> 42) & 0x1FFFFFu) * (1.0 / 2097152.0));
+      double lensq = x * x + y * y + z * z;
+      if (lensq > 1e-160 && lensq <= 1.0) return v3_divs(v3_make(x, y, z), sqrt(lensq));
+    }
   }
 }
 

@@ -308,6 +308,8 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   const int nchunks = (prm->spp + spu - 1) / spu;
   const unsigned long long local_pixels = (unsigned long long)local_rows * (unsigned long long)W;
   const unsigned long long total_units = local_pixels * (unsigned long long)nchunks;
+  if (total_units > 0xffffffffull)
+    return fail(RTCLJ_E_INVALID, "%llu work units: raise samples_per_unit", total_units);
   c->last_spu = spu;
 
   CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), stream));
