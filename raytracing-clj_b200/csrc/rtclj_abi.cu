@@ -84,9 +84,14 @@ struct rtclj_ctx {
 
 namespace {
 
-size_t smem_needed(int nhalf) {
-  return (size_t)nhalf * 256 + (size_t)kListCap * kThreads * 4 + 16;
+// shared memory: [table (large scenes only)] [survivor lists, or 33 per-block masks per lane on the
+// constant-table path] [mbarrier] [unit sums]
+size_t smem_needed(int nhalf, bool const_tab) {
+  const size_t table = const_tab ? 0 : (size_t)nhalf * 256;
+  const size_t lists = (size_t)(const_tab ? 33 : kListCap) * kThreads * 4;
+  return table + lists + 16 + (size_t)kThreads * 24;
 }
+bool use_const_table(int nhalf) { return nhalf * 16 <= kConstSpheres; }
 
 int local_rows_of(int H, int shard_index, int shard_count, int shard_rows) {
   if (shard_count <= 1) return H;
@@ -194,7 +199,8 @@ int rtclj_ctx_create(int32_t device, rtclj_ctx** out) {
   CU(cudaEventCreate(&c->ev2));
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CU(c->counters.reserve(8));
-  CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  CU(cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  CU(cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   *out = c;
   return RTCLJ_OK;
 }
@@ -220,9 +226,9 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
   if (n > 65532) return fail(RTCLJ_E_TOO_LARGE, "%d spheres: survivor lists hold 16-bit indices", n);
   const int nhalf = (n + 15) / 16;  // the cull table is padded to 16-sphere half blocks
   const int npad = nhalf * 16;
-  if (smem_needed(nhalf) > c->smem_optin)
+  if (smem_needed(nhalf, use_const_table(nhalf)) > c->smem_optin)
     return fail(RTCLJ_E_TOO_LARGE, "%d spheres need %zu B of shared memory, device offers %zu", n,
-                smem_needed(nhalf), c->smem_optin);
+                smem_needed(nhalf, false), c->smem_optin);
   for (int i = 0; i < n; ++i) {
     const int k = s->material[i];
     if (k != RTCLJ_LAMBERTIAN && k != RTCLJ_METAL && k != RTCLJ_DIELECTRIC)
@@ -342,8 +348,13 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
       CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
       P.stack = c->stack.p;
     }
-    const size_t smem = smem_needed(c->nhalf);
-    render_kernel<<<grid, kThreads, smem, stream>>>(P);
+    if (use_const_table(c->nhalf)) {
+      // small scene: the cull table goes to constant memory (uniform operands), stream-ordered
+      if (c->nhalf) CU(cudaMemcpyToSymbolAsync(g_ctab, c->geom32.p, (size_t)c->nhalf * 256, 0, cudaMemcpyDeviceToDevice, stream));
+      render_kernel<true><<<grid, kThreads, smem_needed(c->nhalf, true), stream>>>(P);
+    } else {
+      render_kernel<false><<<grid, kThreads, smem_needed(c->nhalf, false), stream>>>(P);
+    }
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(c->ev1, stream));
