@@ -88,8 +88,9 @@ namespace {
 // constant-table path] [mbarrier] [unit sums]
 size_t smem_needed(int nhalf, bool const_tab) {
   const size_t table = const_tab ? 0 : (size_t)nhalf * 256;
-  const size_t lists = (size_t)(const_tab ? 33 : kListCap) * kThreads * 4;
-  return table + lists + 16 + (size_t)kThreads * 24;
+  const size_t threads = (size_t)threads_of(const_tab);
+  const size_t lists = (size_t)(const_tab ? 33 : kListCap) * threads * 4;
+  return table + lists + 16 + threads * 24;
 }
 bool use_const_table(int nhalf) { return nhalf * 16 <= kConstSpheres; }
 
@@ -105,7 +106,7 @@ int local_rows_of(int H, int shard_index, int shard_count, int shard_rows) {
 // Unit size chosen from the image alone (not from the GPU count), so that an image is
 // bit-identical however many GPUs share it: aim at >= 32 units per lane of an 8-GPU box.
 int auto_samples_per_unit(int W, int H, int spp) {
-  const double want_units = 32.0 * 148.0 * kThreads * 8.0;
+  const double want_units = 32.0 * 148.0 * 512.0 * 8.0;
   const double pixels = (double)W * (double)H;
   int nchunks = (int)std::ceil(want_units / pixels);
   nchunks = std::max(1, std::min(nchunks, std::max(1, spp / 8)));
@@ -343,17 +344,18 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
     P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
     P.partial = c->partial.p; P.queue = c->counters.p; P.stats = c->counters.p + 1;
-    P.stack_stride = (unsigned)grid * kThreads;
+    const bool const_tab = use_const_table(c->nhalf);
+    P.stack_stride = (unsigned)grid * (unsigned)threads_of(const_tab);
     if (prm->flags & RTCLJ_F_REVERSE_PRODUCT) {
       CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
       P.stack = c->stack.p;
     }
-    if (use_const_table(c->nhalf)) {
+    if (const_tab) {
       // small scene: the cull table goes to constant memory (uniform operands), stream-ordered
       if (c->nhalf) CU(cudaMemcpyToSymbolAsync(g_ctab, c->geom32.p, (size_t)c->nhalf * 256, 0, cudaMemcpyDeviceToDevice, stream));
-      render_kernel<true><<<grid, kThreads, smem_needed(c->nhalf, true), stream>>>(P);
+      render_kernel<true><<<grid, threads_of(true), smem_needed(c->nhalf, true), stream>>>(P);
     } else {
-      render_kernel<false><<<grid, kThreads, smem_needed(c->nhalf, false), stream>>>(P);
+      render_kernel<false><<<grid, threads_of(false), smem_needed(c->nhalf, false), stream>>>(P);
     }
     CU(cudaGetLastError());
   }

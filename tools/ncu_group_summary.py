@@ -20,7 +20,7 @@ marks = [
     ("cull: packed fp32 wrappers", find("typedef unsigned long long f32x2;"), find("// ---------------------------------------------------------------- TMA bulk staging")),
     ("fp64 div/sqrt (noinline)", find("__noinline__ d3 divs("), find("__noinline__ double dsqrt(") + 1),
     ("helpers: philox", find("uint4 philox("), find("double u24(")),
-    ("helpers: u24/sym/vec3", find("double u24("), find("d3 random_unit(")),
+    ("helpers: u24/sym/vec3", find("double u24("), find("unsigned char quantise(")),
     ("helpers: exact_test", find("void exact_test("), find("__global__ void __launch_bounds__(kThreads")),
     ("staging/init", find("__global__ void __launch_bounds__(kThreads"), find("// ---- refill:")),
     ("refill/unit decode", find("// ---- refill:"), find("// ---- camera ray:")),
