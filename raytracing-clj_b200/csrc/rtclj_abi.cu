@@ -344,7 +344,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
     P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
     P.partial = c->partial.p; P.queue = c->counters.p; P.stats = c->counters.p + 1;
-    const bool const_tab = use_const_table(c->nhalf);
+    const bool const_tab = use_const_table(c->nhalf) && !(prm->flags & RTCLJ_F_SMEM_TABLE);
     P.stack_stride = (unsigned)grid * (unsigned)threads_of(const_tab);
     if (prm->flags & RTCLJ_F_REVERSE_PRODUCT) {
       CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));

@@ -101,6 +101,21 @@ def test_cull_equals_exhaustive_fp64_scan():
     assert sb["exact_tests"] == sb["segments"] * len(world)
 
 
+def test_both_kernels_agree_with_the_oracle():
+    """Scenes of <= 512 spheres normally run the constant-table kernel; RTCLJ_F_SMEM_TABLE sends
+    them through the shared-memory-table kernel (TMA staging, survivor lists, flushes) as well."""
+    for world, cam, flags, seed in (
+            (S.cover_hittables(7), CAM.main_camera(128, 72, **S.COVER_CAMERA), O.FLAGS_MAIN, 3),
+            (S.realm_hittables(), CAM.realm_camera(96), O.FLAGS_REALM, 4),
+            (S.cover_hittables(9)[:17], CAM.main_camera(64, 36, **S.COVER_CAMERA), O.FLAGS_MAIN, 5)):
+        soa = S.to_soa(world)
+        lin_o, rgb_o, st_o = O.render(soa, cam, 8, 50, seed=seed, flags=flags, threads=8, samples_per_unit=8)
+        for extra in (0, _abi.F_SMEM_TABLE):
+            lin_g, rgb_g, st_g = gpu(soa, cam, 8, 50, seed=seed, flags=flags | extra, samples_per_unit=8)
+            assert np.array_equal(lin_o, lin_g) and np.array_equal(rgb_o, rgb_g), extra
+            assert st_g["segments"] == st_o.segments
+
+
 def test_far_origin_and_huge_spheres():
     """Numerics the survey flags (7.3-3): r = 1000 ground, rays leaving from far away."""
     world = S.cover_hittables(5)
