@@ -281,9 +281,17 @@ def main():
     peak_nominal = sms.value * 128 * 2 * sm_max * 1e6 / 1e12
     k_ms = sum(kernel_ms) / len(kernel_ms)
     achieved = seg_local * (FLOP_PER_TEST * n + FLOP_PER_SEGMENT) / (k_ms * 1e-3) / 1e12
+    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == WORKLOAD["name"] and world_size == 1:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s", "frac": achieved / peak_nominal,
-        "traffic": None, "kernel": "render_kernel", "kernel_ms": k_ms,
+        "traffic": traffic, "kernel": "render_kernel", "kernel_ms": k_ms,
         "peak_source": f"{sms.value} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json"
                        f"{'' if peaks else ' MISSING: fallback 1965'}); the path is CUDA-core fp32, not HBM or tensor",
         "peak_calibrated": {"ffma": pk[0].value, "ffma2": pk[1].value, "dfma_fp64": pk[2].value, "unit": "TFLOP/s"},
