@@ -92,7 +92,7 @@ size_t smem_needed(int nhalf, bool const_tab) {
   const size_t lists = (size_t)(const_tab ? 33 : kListCap) * threads * 4;
   return table + lists + 16 + threads * 24;
 }
-bool use_const_table(int nhalf) { return nhalf * 16 <= kConstSpheres; }
+bool use_const_table(int nhalf) { return nhalf * 16 <= 512; }  // <= 32 blocks on that path either way
 
 int local_rows_of(int H, int shard_index, int shard_count, int shard_rows) {
   if (shard_count <= 1) return H;
@@ -226,7 +226,7 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
     return fail(RTCLJ_E_INVALID, "null scene array");
   if (n > 65532) return fail(RTCLJ_E_TOO_LARGE, "%d spheres: survivor lists hold 16-bit indices", n);
   const int nhalf = (n + 15) / 16;  // the cull table is padded to 16-sphere half blocks
-  const int npad = nhalf * 16;
+  const int npad = ((n + 31) / 32) * 32;  // table padded to 32 spheres (the constant-table path may use 16-pair blocks)
   if (smem_needed(nhalf, use_const_table(nhalf)) > c->smem_optin)
     return fail(RTCLJ_E_TOO_LARGE, "%d spheres need %zu B of shared memory, device offers %zu", n,
                 smem_needed(nhalf, false), c->smem_optin);
@@ -340,6 +340,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.W = W; P.H = H; P.spp = prm->spp; P.max_depth = prm->max_depth;
     P.flags = prm->flags; P.k0 = (unsigned)prm->seed; P.k1 = (unsigned)(prm->seed >> 32);
     P.n = c->n; P.nblocks = c->nhalf / 2; P.tail8 = c->nhalf & 1; P.geom_bytes = (unsigned)c->nhalf * 256u;
+    P.nconst = (c->n + 2 * kCBP - 1) / (2 * kCBP);
     P.shard_index = shard_index; P.shard_count = shard_count; P.shard_rows = shard_rows;
     P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
     P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
@@ -352,7 +353,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     }
     if (const_tab) {
       // small scene: the cull table goes to constant memory (uniform operands), stream-ordered
-      if (c->nhalf) CU(cudaMemcpyToSymbolAsync(g_ctab, c->geom32.p, (size_t)c->nhalf * 256, 0, cudaMemcpyDeviceToDevice, stream));
+      if (c->nhalf) CU(cudaMemcpyToSymbolAsync(g_ctab, c->geom32.p, (size_t)((c->n + 31) / 32) * 512, 0, cudaMemcpyDeviceToDevice, stream));
       render_kernel<true><<<grid, threads_of(true), smem_needed(c->nhalf, true), stream>>>(P);
     } else {
       render_kernel<false><<<grid, threads_of(false), smem_needed(c->nhalf, false), stream>>>(P);
