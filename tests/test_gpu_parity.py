@@ -116,6 +116,24 @@ def test_both_kernels_agree_with_the_oracle():
             assert st_g["segments"] == st_o.segments
 
 
+def test_block_boundaries_and_kernel_switch():
+    """Sphere counts around the cull-block sizes (16 / 32) and around 512, where the library
+    switches from the constant-table kernel to the shared-memory-table kernel."""
+    big = S.field_hittables(7, half=14)  # ~780 spheres, same generator as configs 3 and 5
+    assert len(big) > 540
+    cam = CAM.main_camera(48, 27, **S.COVER_CAMERA)
+    for n in (15, 16, 17, 31, 32, 33, 47, 48, 49, 496, 511, 512, 513, 528, 529, 544):
+        world = big[:n - 3] + big[-3:]  # keep the three big spheres in view
+        assert len(world) == n
+        assert_same(world, cam, 6, 50, n, O.FLAGS_MAIN, unit=4)
+
+
+def test_cover_scene_medium_size_bit_exact():
+    assert_same(S.cover_hittables(7), CAM.main_camera(320, 180, **S.COVER_CAMERA), 16, 50, 21, O.FLAGS_MAIN)
+    assert_same(S.cover_hittables(11), CAM.realm_camera(240, 135, look_from=(13.0, 2.0, 3.0), look_at=(0.0, 0.0, 0.0)),
+                16, 50, 22, O.FLAGS_REALM)
+
+
 def test_far_origin_and_huge_spheres():
     """Numerics the survey flags (7.3-3): r = 1000 ground, rays leaving from far away."""
     world = S.cover_hittables(5)
