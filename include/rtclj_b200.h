@@ -56,7 +56,7 @@ enum {
   RTCLJ_E_INVALID = 1,   /* bad argument (null pointer, non-positive size, ...) */
   RTCLJ_E_NO_DEVICE = 2, /* no usable CUDA device: there is no CPU fallback      */
   RTCLJ_E_CUDA = 3,      /* a CUDA call failed; see rtclj_last_error()           */
-  RTCLJ_E_TOO_LARGE = 4, /* scene does not fit the on-chip staging               */
+  RTCLJ_E_TOO_LARGE = 4, /* more than 65 532 spheres                              */
   RTCLJ_E_BUFFER = 5     /* output buffer too small                              */
 };
 

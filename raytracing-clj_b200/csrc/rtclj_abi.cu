@@ -86,8 +86,13 @@ namespace {
 
 // shared memory: [table (large scenes only)] [survivor lists, or 33 per-block masks per lane on the
 // constant-table path] [mbarrier] [unit sums]
-size_t smem_needed(int nhalf, bool const_tab) {
-  const size_t table = const_tab ? 0 : (size_t)nhalf * 256;
+// 16-pair blocks (512 B) of the table that fit in shared memory next to the lists and the sums
+int smem_table_blocks(size_t smem_optin) {
+  const size_t fixed = (size_t)kListCap * threads_of(false) * 4 + 16 + (size_t)threads_of(false) * 24;
+  return smem_optin > fixed ? (int)((smem_optin - fixed) / 512) : 0;
+}
+size_t smem_needed(int nhalf, bool const_tab, size_t smem_optin) {
+  const size_t table = const_tab ? 0 : std::min((size_t)nhalf * 256, (size_t)smem_table_blocks(smem_optin) * 512);
   const size_t threads = (size_t)threads_of(const_tab);
   const size_t lists = (size_t)(const_tab ? 33 : kListCap) * threads * 4;
   return table + lists + 16 + threads * 24;
@@ -227,9 +232,6 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
   if (n > 65532) return fail(RTCLJ_E_TOO_LARGE, "%d spheres: survivor lists hold 16-bit indices", n);
   const int nhalf = (n + 15) / 16;  // the cull table is padded to 16-sphere half blocks
   const int npad = ((n + 31) / 32) * 32;  // table padded to 32 spheres (the constant-table path may use 16-pair blocks)
-  if (smem_needed(nhalf, use_const_table(nhalf)) > c->smem_optin)
-    return fail(RTCLJ_E_TOO_LARGE, "%d spheres need %zu B of shared memory, device offers %zu", n,
-                smem_needed(nhalf, false), c->smem_optin);
   for (int i = 0; i < n; ++i) {
     const int k = s->material[i];
     if (k != RTCLJ_LAMBERTIAN && k != RTCLJ_METAL && k != RTCLJ_DIELECTRIC)
@@ -341,6 +343,8 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.flags = prm->flags; P.k0 = (unsigned)prm->seed; P.k1 = (unsigned)(prm->seed >> 32);
     P.n = c->n; P.nblocks = c->nhalf / 2; P.tail8 = c->nhalf & 1; P.geom_bytes = (unsigned)c->nhalf * 256u;
     P.nconst = (c->n + 2 * kCBP - 1) / (2 * kCBP);
+    P.smem_blocks = smem_table_blocks(c->smem_optin);
+    P.geom_bytes = (unsigned)std::min((size_t)c->nhalf * 256, (size_t)P.smem_blocks * 512);  // staged part
     P.shard_index = shard_index; P.shard_count = shard_count; P.shard_rows = shard_rows;
     P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
     P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
@@ -354,9 +358,9 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     if (const_tab) {
       // small scene: the cull table goes to constant memory (uniform operands), stream-ordered
       if (c->nhalf) CU(cudaMemcpyToSymbolAsync(g_ctab, c->geom32.p, (size_t)((c->n + 31) / 32) * 512, 0, cudaMemcpyDeviceToDevice, stream));
-      render_kernel<true><<<grid, threads_of(true), smem_needed(c->nhalf, true), stream>>>(P);
+      render_kernel<true><<<grid, threads_of(true), smem_needed(c->nhalf, true, c->smem_optin), stream>>>(P);
     } else {
-      render_kernel<false><<<grid, threads_of(false), smem_needed(c->nhalf, false), stream>>>(P);
+      render_kernel<false><<<grid, threads_of(false), smem_needed(c->nhalf, false, c->smem_optin), stream>>>(P);
     }
     CU(cudaGetLastError());
   }

@@ -271,7 +271,18 @@ def test_error_behaviour():
     with pytest.raises(_abi.RtcljError) as e:
         gpu(S.main_hittables(), cam, 1, 5, devices=[99])
     assert e.value.code == _abi.E_INVALID
-    big = S._random_field(1, -80, 80)
+    big = S._random_field(1, -130, 130)  # > 65 532 spheres: survivor entries hold 16-bit block indices
+    assert len(big) > 65532
     with pytest.raises(_abi.RtcljError) as e:
         gpu(big, cam, 1, 5)
     assert e.value.code == _abi.E_TOO_LARGE
+
+
+def test_scene_larger_than_shared_memory():
+    """~25 600 spheres: 410 KB of cull table, of which ~190 KB sit in shared memory and the rest is
+    read from global memory."""
+    world = S._random_field(1, -80, 80)
+    assert len(world) > 25000
+    cam = CAM.main_camera(40, 22, vfov=40.0, look_from=(95.0, 20.0, 30.0), look_at=(0.0, 0.0, 0.0),
+                          defocus_angle=0.3, focus_dist=90.0)
+    assert_same(world, cam, 2, 50, 17, O.FLAGS_MAIN)
