@@ -21,15 +21,15 @@ marks = [
     ("fp64 div/sqrt (noinline)", find("__noinline__ d3 divs("), find("__noinline__ double dsqrt(") + 1),
     ("helpers: philox", find("uint4 philox("), find("double u24(")),
     ("helpers: u24/sym/vec3", find("double u24("), find("unsigned char quantise(")),
-    ("helpers: exact_test", find("void exact_test("), find("__global__ void __launch_bounds__(kThreads")),
-    ("staging/init", find("__global__ void __launch_bounds__(kThreads"), find("// ---- refill:")),
-    ("refill/unit decode", find("// ---- refill:"), find("// ---- camera ray:")),
-    ("camera ray", find("// ---- camera ray:"), find("// ---- fp32 view of the ray")),
+    ("helpers: exact_test", find("void exact_test("), find("template <bool kConstTab>")),
+    ("staging/init", find("template <bool kConstTab>"), find("// ---- fp32 view of the ray")),
     ("cull setup", find("// ---- fp32 view of the ray"), find("// ---- (A)+(B)")),
     ("cull loop+record", find("// ---- (A)+(B)"), find("// ---- (B) exact closest hit")),
-    ("B: list walk+prefilter", find("// ---- (B) exact closest hit"), find("// ---- (C) shade")),
-    ("C: shade", find("// ---- (C) shade"), find("if (done) {")),
-    ("bookkeeping", find("if (done) {"), find("// ---- counters:")),
+    ("B: survivor walk+prefilter", find("// ---- (B) exact closest hit"), find("// ---- (C) shade")),
+    ("C: shade", find("// ---- (C) shade"), find("      if (done) {")),
+    ("bookkeeping", find("      if (done) {"), find("// ---- refill:")),
+    ("refill/unit decode", find("// ---- refill:"), find("// ---- camera ray:")),
+    ("camera ray", find("// ---- camera ray:"), find("// ---- counters:")),
     ("epilogue", find("// ---- counters:"), find("struct FParams")),
 ]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"],
