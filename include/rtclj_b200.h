@@ -18,6 +18,7 @@
  *                           src/raytracing.clj:19-26 ; realm/raytracing.clj:246-249,356-357
  *   rtclj_encode_ppm_p3     the P3 writer, src/raytracing.clj:172-175 ;
  *                           realm/raytracing.clj:350-358
+ *   rtclj_encode_png        ppm->png, src/raytracing.clj:176 (src/ppm2png.clj:35-87)
  *   rtclj_camera_main/_realm/_i
  *                           the camera let-blocks, src/raytracing.clj:105-139 ;
  *                           realm/raytracing.clj:264-280,306-322 ;
@@ -188,6 +189,13 @@ int rtclj_quantise_rgb8(const double *linear, size_t n_values, uint32_t flags, u
  * required capacity in *len. */
 int rtclj_encode_ppm_p3(const uint8_t *rgb8, int32_t width, int32_t height, char *out,
                         size_t capacity, size_t *len);
+
+/* An 8-bit RGB PNG of the same image (what ppm->png produces from the P3 file,
+ * src/raytracing.clj:176 / src/ppm2png.clj:35-87 -- re-implemented from the PNG specification, the
+ * reference file carries a GPL header and nothing of it is used).  Stored (uncompressed) deflate
+ * blocks.  Call with out == NULL to get the required capacity in *len. */
+int rtclj_encode_png(const uint8_t *rgb8, int32_t width, int32_t height, uint8_t *out, size_t capacity,
+                     size_t *len);
 
 /* Clojure's Ratio -> double (Ratio.doubleValue rounds through 16 decimal digits). */
 double rtclj_ratio_to_double(int64_t num, int64_t den);

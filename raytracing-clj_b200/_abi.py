@@ -67,6 +67,8 @@ SYMBOLS = {
     "rtclj_quantise_rgb8": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "rtclj_encode_ppm_p3": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                       C.POINTER(C.c_size_t)]),
+    "rtclj_encode_png": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                   C.POINTER(C.c_size_t)]),
     "rtclj_ratio_to_double": (C.c_double, [C.c_int64, C.c_int64]),
     "rtclj_camera_main": (C.c_int, [C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,

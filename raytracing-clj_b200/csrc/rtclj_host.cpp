@@ -101,6 +101,82 @@ int rtclj_encode_ppm_p3(const uint8_t* rgb8, int32_t width, int32_t height, char
   return RTCLJ_OK;
 }
 
+// ---- PNG (RGB, 8 bit, no interlace) with stored deflate blocks: signature, IHDR, IDAT, IEND.
+namespace {
+struct Crc32 {
+  uint32_t table[256];
+  Crc32() {
+    for (uint32_t n = 0; n < 256; ++n) {
+      uint32_t c = n;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+      table[n] = c;
+    }
+  }
+  uint32_t run(uint32_t crc, const uint8_t* p, size_t n) const {
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+  }
+};
+inline void be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+}  // namespace
+
+int rtclj_encode_png(const uint8_t* rgb8, int32_t width, int32_t height, uint8_t* out, size_t capacity,
+                     size_t* len) {
+  if (width <= 0 || height <= 0 || !len) return RTCLJ_E_INVALID;
+  const size_t row = (size_t)width * 3 + 1;          // filter byte + pixels
+  const size_t raw = row * (size_t)height;           // bytes handed to deflate
+  const size_t nblocks = (raw + 65534) / 65535;      // stored blocks of <= 65535 bytes
+  const size_t zlen = 2 + raw + 5 * nblocks + 4;     // zlib header, blocks, adler32
+  const size_t need = 8 + (12 + 13) + (12 + zlen) + 12;
+  *len = need;
+  if (!out) return RTCLJ_OK;
+  if (!rgb8) return RTCLJ_E_INVALID;
+  if (need > capacity) return RTCLJ_E_BUFFER;
+  if (zlen > 0xffffffffull) return RTCLJ_E_INVALID;
+  static const Crc32 crc;
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  uint8_t* w = out;
+  std::memcpy(w, sig, 8); w += 8;
+  // IHDR
+  be32(w, 13); std::memcpy(w + 4, "IHDR", 4);
+  be32(w + 8, (uint32_t)width); be32(w + 12, (uint32_t)height);
+  w[16] = 8; w[17] = 2; w[18] = 0; w[19] = 0; w[20] = 0;  // 8 bit, truecolour, deflate, no filter method, no interlace
+  be32(w + 21, crc.run(0xffffffffu, w + 4, 17) ^ 0xffffffffu);
+  w += 25;
+  // IDAT
+  be32(w, (uint32_t)zlen); std::memcpy(w + 4, "IDAT", 4);
+  uint8_t* z = w + 8;
+  z[0] = 0x78; z[1] = 0x01;
+  uint8_t* q = z + 2;
+  uint32_t a = 1, b = 0;  // adler32 over the raw stream
+  size_t produced = 0, in_block = 0;
+  auto emit = [&](uint8_t v) {
+    if (in_block == 0) {
+      const size_t left = raw - produced, n = left < 65535 ? left : 65535;
+      q[0] = (produced + n == raw) ? 1 : 0;  // BFINAL, BTYPE = 00 (stored)
+      q[1] = (uint8_t)(n & 0xff); q[2] = (uint8_t)(n >> 8); q[3] = (uint8_t)~q[1]; q[4] = (uint8_t)~q[2];
+      q += 5;
+      in_block = n;
+    }
+    *q++ = v;
+    --in_block; ++produced;
+    a += v; if (a >= 65521u) a -= 65521u;
+    b += a; if (b >= 65521u) b -= 65521u;
+  };
+  for (int32_t j = 0; j < height; ++j) {
+    emit(0);  // filter type None
+    const uint8_t* src = rgb8 + (size_t)j * (size_t)width * 3;
+    for (size_t i = 0; i < (size_t)width * 3; ++i) emit(src[i]);
+  }
+  be32(q, (b << 16) | a); q += 4;
+  be32(q, crc.run(0xffffffffu, w + 4, 4 + zlen) ^ 0xffffffffu);
+  w = q + 4;
+  // IEND
+  be32(w, 0); std::memcpy(w + 4, "IEND", 4);
+  be32(w + 8, crc.run(0xffffffffu, w + 4, 4) ^ 0xffffffffu);
+  return RTCLJ_OK;
+}
+
 // clojure.lang.Ratio.doubleValue: BigDecimal(num).divide(BigDecimal(den), DECIMAL64).doubleValue(),
 // i.e. the quotient rounded HALF_EVEN to 16 significant decimal digits, then to double
 // (SURVEY.md Appendix B.1).  Integral quotients are Longs in Clojure and stay exact.

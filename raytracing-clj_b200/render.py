@@ -149,6 +149,23 @@ def encode_ppm(rgb8: np.ndarray) -> bytes:
     return buf.raw[: n.value]
 
 
+def encode_png(rgb8: np.ndarray) -> bytes:
+    """The PNG `ppm->png` writes next to the PPM (raytracing.clj:176)."""
+    img = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    H, W, _ = img.shape
+    n = C.c_size_t()
+    lib = _abi.lib()
+    _abi.check(lib.rtclj_encode_png(None, W, H, None, 0, C.byref(n)))
+    buf = (C.c_uint8 * n.value)()
+    _abi.check(lib.rtclj_encode_png(img.ctypes.data, W, H, buf, n.value, C.byref(n)))
+    return bytes(buf[: n.value])
+
+
+def write_png(path: str, rgb8: np.ndarray) -> None:
+    with open(path, "wb") as f:
+        f.write(encode_png(rgb8))
+
+
 def write_ppm(path: str, rgb8: np.ndarray) -> None:
     with open(path, "wb") as f:
         f.write(encode_ppm(rgb8))

@@ -98,6 +98,23 @@ def test_ppm_of_reference_golden_round_trips():
     assert len(text) == 90003 + 1                              # 90 003 lines
 
 
+def test_png_encoder_decodes_to_the_same_pixels():
+    import io
+    from PIL import Image
+    rng = np.random.default_rng(1)
+    for shape in ((5, 7, 3), (1, 1, 3), (225, 400, 3), (300, 30000 // 3, 3)):  # the last one spans several 64 KiB blocks
+        img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        png = render.encode_png(img)
+        assert png[:8] == b"\x89PNG\r\n\x1a\n"
+        back = np.asarray(Image.open(io.BytesIO(png)).convert("RGB"))
+        assert back.shape == img.shape and np.array_equal(back, img)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_images.npz"))["scene_main"]
+    back = np.asarray(Image.open(io.BytesIO(render.encode_png(gold))))
+    assert np.array_equal(back, gold)  # like scene.png vs scene.ppm in the reference
+    n = C.c_size_t()
+    assert _abi.lib().rtclj_encode_png(gold.ctypes.data, 400, 225, (C.c_uint8 * 16)(), 16, C.byref(n)) == _abi.E_BUFFER
+
+
 def test_native_scene_generator_equals_python_generator():
     lib = _abi.lib()
     for seed, lo, hi in ((7, -11, 11), (3, -11, 11), (7, -50, 50), (1, 0, 0)):
