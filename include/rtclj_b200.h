@@ -17,7 +17,9 @@
  *   rtclj_quantise_rgb8     write-color! / linear->gamma / clamp,
  *                           src/raytracing.clj:19-26 ; realm/raytracing.clj:246-249,356-357
  *   rtclj_encode_ppm_p3     the P3 writer, src/raytracing.clj:172-175 ;
- *                           realm/raytracing.clj:350-358
+ *                           realm/raytracing.clj:350-358 (host)
+ *   rtclj_ctx_encode_ppm_p3, rtclj_encode_ppm_p3_gpu
+ *                           the same writer as device kernels (device / host buffers)
  *   rtclj_encode_png        ppm->png, src/raytracing.clj:176 (src/ppm2png.clj:35-87)
  *   rtclj_camera_main/_realm/_i
  *                           the camera let-blocks, src/raytracing.clj:105-139 ;
@@ -185,10 +187,23 @@ int rtclj_calibrate_peaks(int32_t device, double *ffma_tflops, double *ffma2_tfl
 /* write-color!: 3 linear doubles -> 3 ints in 0..255 per pixel (host). */
 int rtclj_quantise_rgb8(const double *linear, size_t n_values, uint32_t flags, uint8_t *out);
 
-/* "P3\nW H\n255\n" + one "r g b\n" line per pixel.  Call with out == NULL to get the
- * required capacity in *len. */
+/* "P3\nW H\n255\n" + one "r g b\n" line per pixel.  Call with out == NULL to get a sufficient
+ * capacity (an upper bound) in *len; the full call sets *len to the bytes written. */
 int rtclj_encode_ppm_p3(const uint8_t *rgb8, int32_t width, int32_t height, char *out,
                         size_t capacity, size_t *len);
+
+/* The same writer as kernels on the device (row f-1 of SURVEY.md section 8: at 3840x2160 the text is
+ * 89 MB and a host writer costs more than the render of a primary-ray image).  d_rgb8 and d_out are
+ * DEVICE pointers; the bytes produced are identical to rtclj_encode_ppm_p3's.  d_out == NULL is a
+ * sizing call that returns the exact length.  Synchronises `stream` before returning (the length
+ * comes back from the device).  rtclj_ctx_encode_ms reports the device time of the last call's
+ * two phases (line lengths + scan; text write). */
+int rtclj_ctx_encode_ppm_p3(rtclj_ctx *ctx, const uint8_t *d_rgb8, int32_t width, int32_t height,
+                            char *d_out, size_t capacity, size_t *len, void *stream);
+int rtclj_ctx_encode_ms(rtclj_ctx *ctx, double *count_scan_ms, double *write_ms);
+/* Host buffers in and out, the encoding on `device` (copies inside the call). */
+int rtclj_encode_ppm_p3_gpu(int32_t device, const uint8_t *rgb8, int32_t width, int32_t height,
+                            char *out, size_t capacity, size_t *len);
 
 /* An 8-bit RGB PNG of the same image (what ppm->png produces from the P3 file,
  * src/raytracing.clj:176 / src/ppm2png.clj:35-87 -- re-implemented from the PNG specification, the

@@ -67,6 +67,11 @@ SYMBOLS = {
     "rtclj_quantise_rgb8": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "rtclj_encode_ppm_p3": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                       C.POINTER(C.c_size_t)]),
+    "rtclj_encode_ppm_p3_gpu": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                          C.POINTER(C.c_size_t)]),
+    "rtclj_ctx_encode_ppm_p3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                          C.POINTER(C.c_size_t), C.c_void_p]),
+    "rtclj_ctx_encode_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rtclj_encode_png": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_size_t)]),
     "rtclj_ratio_to_double": (C.c_double, [C.c_int64, C.c_int64]),

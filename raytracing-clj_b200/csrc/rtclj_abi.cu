@@ -3,6 +3,7 @@
 // table), work-unit sizing, launches, copies.  No CPU fallback anywhere in this file.
 #include "../../include/rtclj_b200.h"
 #include "rtclj_kernels.cuh"
+#include "rtclj_p3_kernels.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -76,6 +77,10 @@ struct rtclj_ctx {
   DevBuf<unsigned short> stack;
   DevBuf<double> out_linear;            // used by the host-buffer entry points
   DevBuf<unsigned char> out_rgb8;
+  DevBuf<unsigned long long> p3_state;  // P3 writer: ticket, total, text bytes per CTA run
+  int p3_ctas_per_sm = 0;
+  DevBuf<unsigned char> p3_in, p3_text; // staging for the host-buffer entry point
+  float p3_count_ms = 0.f, p3_write_ms = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   cudaStream_t own_stream = nullptr;
   int last_spu = 0;
@@ -216,6 +221,7 @@ void rtclj_ctx_destroy(rtclj_ctx* c) {
   cudaSetDevice(c->device);
   c->geom32.release(); c->geom64.release(); c->mat.release(); c->partial.release();
   c->counters.release(); c->stack.release(); c->out_linear.release(); c->out_rgb8.release();
+  c->p3_state.release(); c->p3_in.release(); c->p3_text.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -517,6 +523,88 @@ int rtclj_render(const rtclj_scene* scene, const rtclj_camera* cam, const rtclj_
   }
   const int32_t dev = prm->device;
   return rtclj_render_multi(scene, cam, prm, &dev, 1, out_linear, out_rgb8, stats);
+}
+
+// ---- row f-1: the P3 writer (src/raytracing.clj:172-175) on the device
+int rtclj_ctx_encode_ppm_p3(rtclj_ctx* c, const uint8_t* d_rgb8, int32_t width, int32_t height, char* d_out,
+                            size_t capacity, size_t* len, void* stream_) {
+  if (!c) return fail(RTCLJ_E_INVALID, "null ctx");
+  if (width <= 0 || height <= 0 || !len || !d_rgb8) return fail(RTCLJ_E_INVALID, "bad image or null len");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CU(cudaSetDevice(c->device));
+  const size_t npix = (size_t)width * (size_t)height;
+  const size_t nb = (npix + kP3PixPerBlock - 1) / kP3PixPerBlock;
+  if (nb > 0x7fffffffull) return fail(RTCLJ_E_TOO_LARGE, "image of %zu pixels is too large for the P3 writer", npix);
+  P3Header hdr;
+  hdr.n = std::snprintf(hdr.s, sizeof hdr.s, "P3\n%d %d\n255\n", width, height);
+  const int aligned4 = (reinterpret_cast<uintptr_t>(d_rgb8) & 3u) == 0;
+  // persistent grid: every CTA owns one contiguous run of tiles
+  if (c->p3_ctas_per_sm == 0) {
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p3_encode_kernel, kP3Threads, 0));
+    c->p3_ctas_per_sm = occ > 0 ? occ : 1;
+  }
+  const size_t want = (size_t)c->sm_count * (size_t)c->p3_ctas_per_sm;
+  const size_t per_cta = (nb + want - 1) / want;
+  const size_t grid = (nb + per_cta - 1) / per_cta;
+  CU(c->p3_state.reserve(grid + 2));
+  unsigned long long total = 0;
+  const bool one_pass = d_out && capacity >= (size_t)hdr.n + npix * 12;  // the buffer holds the worst case
+  c->p3_count_ms = c->p3_write_ms = 0.f;
+  if (!one_pass) {  // the exact length first: sizing calls and tighter buffers
+    CU(cudaMemsetAsync(c->p3_state.p, 0, (grid + 2) * sizeof(unsigned long long), stream));
+    CU(cudaEventRecord(c->ev0, stream));
+    p3_encode_kernel<<<(unsigned)grid, kP3Threads, 0, stream>>>(d_rgb8, npix, aligned4, nb, per_cta, c->p3_state.p, nullptr, hdr, 1);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev2, stream));
+    CU(cudaMemcpyAsync(&total, c->p3_state.p + 1, sizeof total, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaEventElapsedTime(&c->p3_count_ms, c->ev0, c->ev2));
+    *len = (size_t)total;
+    if (!d_out) return RTCLJ_OK;
+    if ((size_t)total > capacity) return fail(RTCLJ_E_BUFFER, "P3 text needs %llu bytes, capacity is %zu", total, capacity);
+  }
+  CU(cudaMemsetAsync(c->p3_state.p, 0, (grid + 2) * sizeof(unsigned long long), stream));
+  CU(cudaEventRecord(c->ev0, stream));
+  p3_encode_kernel<<<(unsigned)grid, kP3Threads, 0, stream>>>(d_rgb8, npix, aligned4, nb, per_cta, c->p3_state.p,
+                                                            reinterpret_cast<unsigned char*>(d_out), hdr, 0);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev1, stream));
+  CU(cudaMemcpyAsync(&total, c->p3_state.p + 1, sizeof total, cudaMemcpyDeviceToHost, stream));
+  CU(cudaStreamSynchronize(stream));
+  CU(cudaEventElapsedTime(&c->p3_write_ms, c->ev0, c->ev1));
+  *len = (size_t)total;
+  return RTCLJ_OK;
+}
+
+int rtclj_ctx_encode_ms(rtclj_ctx* c, double* count_scan_ms, double* write_ms) {
+  if (!c) return fail(RTCLJ_E_INVALID, "null ctx");
+  if (count_scan_ms) *count_scan_ms = (double)c->p3_count_ms;
+  if (write_ms) *write_ms = (double)c->p3_write_ms;
+  return RTCLJ_OK;
+}
+
+int rtclj_encode_ppm_p3_gpu(int32_t device, const uint8_t* rgb8, int32_t width, int32_t height, char* out,
+                            size_t capacity, size_t* len) {
+  if (width <= 0 || height <= 0 || !len || !rgb8) return fail(RTCLJ_E_INVALID, "bad image or null len");
+  rtclj_ctx* c = nullptr;
+  int rc = cached_ctx(device, &c);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  const size_t npix = (size_t)width * (size_t)height;
+  CU(c->p3_in.reserve(npix * 3));
+  CU(cudaMemcpyAsync(c->p3_in.p, rgb8, npix * 3, cudaMemcpyHostToDevice, c->own_stream));
+  size_t need = 0;
+  if (!out) return rtclj_ctx_encode_ppm_p3(c, c->p3_in.p, width, height, nullptr, 0, len, c->own_stream);
+  const size_t worst = 64 + npix * 12;  // "255 255 255\n" per pixel
+  CU(c->p3_text.reserve(worst));
+  rc = rtclj_ctx_encode_ppm_p3(c, c->p3_in.p, width, height, reinterpret_cast<char*>(c->p3_text.p),
+                               std::min(worst, capacity), &need, c->own_stream);
+  *len = need;
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, c->p3_text.p, need, cudaMemcpyDeviceToHost, c->own_stream));
+  CU(cudaStreamSynchronize(c->own_stream));
+  return RTCLJ_OK;
 }
 
 int rtclj_calibrate_peaks(int32_t device, double* ffma, double* ffma2, double* dfma, int32_t* sm_count) {

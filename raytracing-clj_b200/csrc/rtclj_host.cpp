@@ -75,46 +75,81 @@ int rtclj_encode_ppm_p3(const uint8_t* rgb8, int32_t width, int32_t height, char
   char header[64];
   const int hl = std::snprintf(header, sizeof header, "P3\n%d %d\n255\n", width, height);
   const size_t npix = (size_t)width * (size_t)height;
-  if (!out) {  // sizing call: worst case "255 255 255\n"
-    *len = (size_t)hl + npix * 12;
+  if (!out) {  // sizing call: worst case "255 255 255\n" (+4: room for the one-pass writer's wide copies)
+    *len = (size_t)hl + npix * 12 + 4;
     return RTCLJ_OK;
   }
   if (!rgb8) return RTCLJ_E_INVALID;
+  // "ddd" + separator slot, and the digit count, per byte value
   static const struct Lut { char s[256][4]; unsigned char n[256]; Lut() {
-      for (int v = 0; v < 256; ++v) n[v] = (unsigned char)std::snprintf(s[v], 4, "%d", v);
+      for (int v = 0; v < 256; ++v) { n[v] = (unsigned char)std::snprintf(s[v], 4, "%d", v); s[v][n[v]] = ' '; }
     } } lut;
-  size_t need = (size_t)hl;
-  for (size_t i = 0; i < npix * 3; ++i) need += lut.n[rgb8[i]] + 1u;
-  *len = need;
-  if (need > capacity) return RTCLJ_E_BUFFER;
+  const size_t worst = (size_t)hl + npix * 12;
+  size_t need = worst;
+  if (capacity < worst + 4) {  // not provably large enough: measure first
+    need = (size_t)hl;
+    for (size_t i = 0; i < npix * 3; ++i) need += lut.n[rgb8[i]] + 1u;
+    *len = need;
+    if (need > capacity) return RTCLJ_E_BUFFER;
+  }
   std::memcpy(out, header, (size_t)hl);
   char* w = out + hl;
-  for (size_t p = 0; p < npix; ++p) {
+  // 4-byte copies of "ddd " overrun the text by at most 3 bytes; the last pixels go bytewise
+  const size_t safe = (capacity >= worst + 4) ? npix : (npix > 2 ? npix - 2 : 0);
+  const uint8_t* src = rgb8;
+  for (size_t p = 0; p < safe; ++p, src += 3) {
+    const unsigned r = src[0], g = src[1], b = src[2];
+    std::memcpy(w, lut.s[r], 4); w += lut.n[r] + 1u;
+    std::memcpy(w, lut.s[g], 4); w += lut.n[g] + 1u;
+    std::memcpy(w, lut.s[b], 4); w += lut.n[b];
+    *w++ = '\n';
+  }
+  for (size_t p = safe; p < npix; ++p, src += 3) {
     for (int ch = 0; ch < 3; ++ch) {
-      const unsigned v = rgb8[3 * p + ch];
-      const unsigned n = lut.n[v];
-      w[0] = lut.s[v][0]; if (n > 1) w[1] = lut.s[v][1]; if (n > 2) w[2] = lut.s[v][2];
-      w += n;
+      const unsigned v = src[ch], n = lut.n[v];
+      for (unsigned k = 0; k < n; ++k) *w++ = lut.s[v][k];
       *w++ = ch == 2 ? '\n' : ' ';
     }
   }
+  *len = (size_t)(w - out);
   return RTCLJ_OK;
 }
 
 // ---- PNG (RGB, 8 bit, no interlace) with stored deflate blocks: signature, IHDR, IDAT, IEND.
 namespace {
-struct Crc32 {
-  uint32_t table[256];
+struct Crc32 {  // slicing-by-8 over the reflected polynomial 0xEDB88320
+  uint32_t table[8][256];
   Crc32() {
     for (uint32_t n = 0; n < 256; ++n) {
       uint32_t c = n;
       for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-      table[n] = c;
+      table[0][n] = c;
     }
+    for (uint32_t n = 0; n < 256; ++n)
+      for (int t = 1; t < 8; ++t) table[t][n] = table[0][table[t - 1][n] & 0xffu] ^ (table[t - 1][n] >> 8);
   }
   uint32_t run(uint32_t crc, const uint8_t* p, size_t n) const {
-    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    while (n >= 8) {
+      uint32_t lo, hi;
+      std::memcpy(&lo, p, 4); std::memcpy(&hi, p + 4, 4);  // little-endian hosts (x86-64, aarch64)
+      lo ^= crc;
+      crc = table[7][lo & 0xffu] ^ table[6][(lo >> 8) & 0xffu] ^ table[5][(lo >> 16) & 0xffu] ^ table[4][lo >> 24] ^
+            table[3][hi & 0xffu] ^ table[2][(hi >> 8) & 0xffu] ^ table[1][(hi >> 16) & 0xffu] ^ table[0][hi >> 24];
+      p += 8; n -= 8;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[0][(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
     return crc;
+  }
+};
+struct Adler32 {  // sums reduced every 5552 bytes, the longest run that cannot overflow 32 bits
+  uint32_t a = 1, b = 0;
+  void run(const uint8_t* p, size_t n) {
+    while (n) {
+      const size_t k = n < 5552 ? n : 5552;
+      for (size_t i = 0; i < k; ++i) { a += p[i]; b += a; }
+      a %= 65521u; b %= 65521u;
+      p += k; n -= k;
+    }
   }
 };
 inline void be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
@@ -148,27 +183,30 @@ int rtclj_encode_png(const uint8_t* rgb8, int32_t width, int32_t height, uint8_t
   uint8_t* z = w + 8;
   z[0] = 0x78; z[1] = 0x01;
   uint8_t* q = z + 2;
-  uint32_t a = 1, b = 0;  // adler32 over the raw stream
+  // the raw stream (filter byte 0 + the row, per row) cut into stored blocks of <= 65535 bytes
+  Adler32 adler;
   size_t produced = 0, in_block = 0;
-  auto emit = [&](uint8_t v) {
-    if (in_block == 0) {
-      const size_t left = raw - produced, n = left < 65535 ? left : 65535;
-      q[0] = (produced + n == raw) ? 1 : 0;  // BFINAL, BTYPE = 00 (stored)
-      q[1] = (uint8_t)(n & 0xff); q[2] = (uint8_t)(n >> 8); q[3] = (uint8_t)~q[1]; q[4] = (uint8_t)~q[2];
-      q += 5;
-      in_block = n;
+  auto emit = [&](const uint8_t* p, size_t n) {
+    adler.run(p, n);
+    while (n) {
+      if (in_block == 0) {
+        const size_t left = raw - produced, m = left < 65535 ? left : 65535;
+        q[0] = (produced + m == raw) ? 1 : 0;  // BFINAL, BTYPE = 00 (stored)
+        q[1] = (uint8_t)(m & 0xff); q[2] = (uint8_t)(m >> 8); q[3] = (uint8_t)~q[1]; q[4] = (uint8_t)~q[2];
+        q += 5;
+        in_block = m;
+      }
+      const size_t k = n < in_block ? n : in_block;
+      std::memcpy(q, p, k);
+      q += k; p += k; n -= k; in_block -= k; produced += k;
     }
-    *q++ = v;
-    --in_block; ++produced;
-    a += v; if (a >= 65521u) a -= 65521u;
-    b += a; if (b >= 65521u) b -= 65521u;
   };
+  static const uint8_t filter_none = 0;
   for (int32_t j = 0; j < height; ++j) {
-    emit(0);  // filter type None
-    const uint8_t* src = rgb8 + (size_t)j * (size_t)width * 3;
-    for (size_t i = 0; i < (size_t)width * 3; ++i) emit(src[i]);
+    emit(&filter_none, 1);
+    emit(rgb8 + (size_t)j * (size_t)width * 3, (size_t)width * 3);
   }
-  be32(q, (b << 16) | a); q += 4;
+  be32(q, (adler.b << 16) | adler.a); q += 4;
   be32(q, crc.run(0xffffffffu, w + 4, 4 + zlen) ^ 0xffffffffu);
   w = q + 4;
   // IEND

@@ -117,6 +117,22 @@ class Context:
         _abi.check(_abi.lib().rtclj_ctx_stats(self._h, C.c_void_p(stream or None), C.byref(st)))
         return st.as_dict()
 
+    def encode_ppm(self, d_rgb8: int, width: int, height: int, d_out: int = 0, capacity: int = 0,
+                   stream: int = 0) -> int:
+        """The P3 writer (raytracing.clj:172-175) as device kernels: d_rgb8 -> text at d_out, both
+        device pointers.  d_out = 0 is the sizing call.  Returns the text length in bytes."""
+        n = C.c_size_t()
+        _abi.check(_abi.lib().rtclj_ctx_encode_ppm_p3(self._h, C.c_void_p(d_rgb8), int(width), int(height),
+                                                      C.c_void_p(d_out or None), int(capacity), C.byref(n),
+                                                      C.c_void_p(stream or None)))
+        return n.value
+
+    def encode_ms(self) -> tuple:
+        """(line lengths + scan, text write) device milliseconds of the last encode_ppm call."""
+        a, b = C.c_double(), C.c_double()
+        _abi.check(_abi.lib().rtclj_ctx_encode_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def close(self) -> None:
         if self._h:
             _abi.lib().rtclj_ctx_destroy(self._h)
@@ -137,28 +153,32 @@ def quantise_rgb8(linear: np.ndarray, flags: int = 0) -> np.ndarray:
     return out
 
 
-def encode_ppm(rgb8: np.ndarray) -> bytes:
-    """"P3\\nW H\\n255\\n" then one "r g b\\n" line per pixel (raytracing.clj:172-175)."""
-    img = np.ascontiguousarray(rgb8, dtype=np.uint8)
+def _two_call(fn, img: np.ndarray, *lead) -> bytes:
+    """Sizing call, then the real call into a caller-owned buffer."""
     H, W, _ = img.shape
     n = C.c_size_t()
+    _abi.check(fn(*lead, img.ctypes.data, W, H, None, 0, C.byref(n)))
+    store = bytearray(n.value)
+    buf = (C.c_char * n.value).from_buffer(store)
+    _abi.check(fn(*lead, img.ctypes.data, W, H, buf, n.value, C.byref(n)))
+    del buf
+    return bytes(memoryview(store)[: n.value])
+
+
+def encode_ppm(rgb8: np.ndarray, device: int | None = None) -> bytes:
+    """"P3\\nW H\\n255\\n" then one "r g b\\n" line per pixel (raytracing.clj:172-175).
+    device = None: the host encoder; device = k: the encoder kernels on GPU k (same bytes)."""
+    img = np.ascontiguousarray(rgb8, dtype=np.uint8)
     lib = _abi.lib()
-    _abi.check(lib.rtclj_encode_ppm_p3(None, W, H, None, 0, C.byref(n)))
-    buf = C.create_string_buffer(n.value)
-    _abi.check(lib.rtclj_encode_ppm_p3(img.ctypes.data, W, H, buf, n.value, C.byref(n)))
-    return buf.raw[: n.value]
+    if device is None:
+        return _two_call(lib.rtclj_encode_ppm_p3, img)
+    return _two_call(lib.rtclj_encode_ppm_p3_gpu, img, int(device))
 
 
 def encode_png(rgb8: np.ndarray) -> bytes:
     """The PNG `ppm->png` writes next to the PPM (raytracing.clj:176)."""
     img = np.ascontiguousarray(rgb8, dtype=np.uint8)
-    H, W, _ = img.shape
-    n = C.c_size_t()
-    lib = _abi.lib()
-    _abi.check(lib.rtclj_encode_png(None, W, H, None, 0, C.byref(n)))
-    buf = (C.c_uint8 * n.value)()
-    _abi.check(lib.rtclj_encode_png(img.ctypes.data, W, H, buf, n.value, C.byref(n)))
-    return bytes(buf[: n.value])
+    return _two_call(_abi.lib().rtclj_encode_png, img)
 
 
 def write_png(path: str, rgb8: np.ndarray) -> None:
@@ -166,6 +186,6 @@ def write_png(path: str, rgb8: np.ndarray) -> None:
         f.write(encode_png(rgb8))
 
 
-def write_ppm(path: str, rgb8: np.ndarray) -> None:
+def write_ppm(path: str, rgb8: np.ndarray, device: int | None = None) -> None:
     with open(path, "wb") as f:
-        f.write(encode_ppm(rgb8))
+        f.write(encode_ppm(rgb8, device))

@@ -91,6 +91,32 @@ def test_ppm_encoder_matches_reference_format():
     assert _abi.lib().rtclj_encode_ppm_p3(img.ctypes.data, 7, 5, buf, 8, C.byref(n)) == _abi.E_BUFFER and n.value > 8
 
 
+def test_ppm_encoder_exact_capacity_and_one_pass_paths_agree():
+    """The host writer has a measuring path (tight buffer) and a one-pass path (worst-case buffer)."""
+    rng = np.random.default_rng(2)
+    for shape in ((1, 1), (1, 2), (3, 5), (64, 33)):
+        img = rng.integers(0, 256, size=shape + (3,), dtype=np.uint8)
+        want = ("P3\n%d %d\n255\n" % (shape[1], shape[0]) + "".join("%d %d %d\n" % tuple(px) for px in img.reshape(-1, 3).tolist())).encode()
+        n = C.c_size_t()
+        for cap in (len(want), len(want) + 1, len(want) + 3, 64 + 12 * shape[0] * shape[1]):
+            buf = C.create_string_buffer(b"\xaa" * (cap + 8), cap + 8)
+            assert _abi.lib().rtclj_encode_ppm_p3(img.ctypes.data, shape[1], shape[0], buf, cap, C.byref(n)) == 0
+            assert n.value == len(want) and buf.raw[: n.value] == want
+            assert buf.raw[cap:] == b"\xaa" * 8                      # nothing past the stated capacity
+
+
+def test_device_ppm_writer_formatting_primitives(tmp_path):
+    """The device P3 writer's byte-parallel digit / length / packing helpers, checked on the CPU:
+    exhaustively over value pairs, and against sprintf for random threads' worth of pixels."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "p3_swar_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(root, "raytracing-clj_b200", "csrc"),
+                    "-o", exe, os.path.join(root, "tests", "native", "p3_swar_check.cpp")], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == "ok"
+
+
 def test_ppm_of_reference_golden_round_trips():
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_images.npz"))["scene_main"]
     text = render.encode_ppm(gold).decode().split("\n")
