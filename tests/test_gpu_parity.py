@@ -177,6 +177,29 @@ def test_edge_cases():
     assert_same(tie, CAM.i_camera(48), 4, 50, 1, O.FLAGS_REALM)
 
 
+def test_parameters_outside_the_reference_scenes():
+    """Values the reference's constructors accept without checks (hittable.clj:7, material.clj:13-36):
+    negative radius (the book's hollow-glass trick: flips the outward normal), zero radius, fuzz > 1,
+    ior = 1 and ior < 1, albedo outside [0,1], coincident centres with different radii."""
+    sp, mat = R.hittable.sphere, R.material
+    world = [S.body(sp((0, -100.5, -1), 100.0), mat.lambertian((0.8, 0.8, 0.0))),
+             S.body(sp((-1.0, 0, -1), 0.5), mat.dielectric(1.5)),
+             S.body(sp((-1.0, 0, -1), -0.4), mat.dielectric(1.5)),          # hollow glass, book style
+             S.body(sp((0.0, 0, -1.2), 0.5), mat.metal((1.3, 0.6, -0.1), 1.7)),
+             S.body(sp((1.0, 0, -1), 0.5), mat.dielectric(1.0)),
+             S.body(sp((1.0, 0.9, -1), 0.3), mat.dielectric(0.4)),
+             S.body(sp((0.3, 0.1, -0.4), 0.0), mat.lambertian((0.5, 0.5, 0.5))),
+             S.body(sp((0.0, 0.8, -1.2), -0.25), mat.lambertian((0.2, 0.9, 0.4))),
+             S.body(sp((0.0, 0.8, -1.2), 0.1), mat.metal((0.9, 0.9, 0.9), 0.0))]
+    for flags in (O.FLAGS_MAIN, O.FLAGS_REALM):
+        assert_same(world, CAM.main_camera(80), 16, 50, 21, flags)
+        assert_same(world, CAM.i_camera(64), 8, 50, 22, flags)
+    # camera inside a negative-radius sphere
+    inside = [S.body(sp((0, 0, 0), -30.0), mat.lambertian((0.7, 0.7, 0.7))),
+              S.body(sp((0, 0, -1), 0.5), mat.dielectric(1.5))]
+    assert_same(inside, CAM.i_camera(48), 8, 50, 23, O.FLAGS_MAIN)
+
+
 def test_depth_cap_and_deep_paths():
     # a mirror box: paths bounce until the depth cap; exercises the reverse-product stack
     walls = [S.body(R.hittable.sphere((0, 0, 0), 50.0), R.material.metal((0.99, 0.98, 0.97), 0.0)),
