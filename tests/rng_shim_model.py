@@ -1,5 +1,5 @@
 """Python model of integration/clojure/src/rtclj/rng_shim.clj plus a sequential-`rand` restatement of the
-reference's `main` render loop, used to check that the shim's hand-out order reproduces the
+reference's `main` and `realm` render loops, used to check that the shim's hand-out order reproduces the
 counter-based stream of oracle/rt_oracle.c.
 
 Test infrastructure only (pure-Python loops: tiny images).  `ShimStream` mirrors the Clojure state
@@ -90,9 +90,11 @@ def refract(uv, n, eta):
     return add(perp, para)
 
 
-def render_main(soa, cam, spp, max_depth, seed=1):
-    """The `main` variant (Schlick, near-zero guard, defocus disk, innermost-first product, / spp),
-    sequential draws.  Returns (linear [H][W] of 3-tuples, segments traced, Philox blocks drawn)."""
+def render_main(soa, cam, spp, max_depth, seed=1, realm=False):
+    """The `main` variant (Schlick, near-zero guard, defocus disk, innermost-first product, / spp) or,
+    with realm=True, the `realm` variant (none of the first three, forward product as
+    realm/raytracing.clj:205-236 multiplies it, x (1/spp)); sequential draws either way.
+    Returns (linear [H][W] of 3-tuples, segments traced, Philox blocks drawn)."""
     center, radius, kind, albedo, fuzz, ior = (x.tolist() for x in soa)
     st = ShimStream(seed)
     rand = st.rand
@@ -138,45 +140,67 @@ def render_main(soa, cam, spp, max_depth, seed=1):
         front = dot(d, outward) < 0.0
         return best, p, (outward if front else neg(outward)), front
 
-    def ray_color(o, d, depth):                    # raytracing.clj:45-58
-        st.set_stage(max_depth - depth + 1)        # the shim's hook: draws of this call belong to this hit
+    BLACK = (0.0, 0.0, 0.0)
+
+    def bounce(o, d, depth):
+        """One level of ray-color (raytracing.clj:45-58): ("black",) | ("sky", colour) |
+        ("scatter", point, direction, attenuation)."""
+        st.set_stage(max_depth - depth + 1)        # the shim's hook: draws of this level belong to this hit
         if depth <= 0:
-            return (0.0, 0.0, 0.0)
+            return ("black",)
         segments[0] += 1
         rec = hit_anything(o, d, 1e-3, math.inf)
         if rec is None:
             y = unit(d)[1]
             a = 0.5 * (y + 1.0)
-            return add(muls((1.0, 1.0, 1.0), 1.0 - a), muls((0.5, 0.7, 1.0), a))
+            return ("sky", add(muls((1.0, 1.0, 1.0), 1.0 - a), muls((0.5, 0.7, 1.0), a)))
         b, p, n, front = rec
-        if kind[b] == 0:                           # lambertian, material.clj:13-19
+        if kind[b] == 0:                           # lambertian, material.clj:13-19 / realm :138-145
             s = add(random_unit_vec3(), n)
-            if abs(s[0]) < 1e-8 and abs(s[1]) < 1e-8 and abs(s[2]) < 1e-8:
+            if not realm and abs(s[0]) < 1e-8 and abs(s[1]) < 1e-8 and abs(s[2]) < 1e-8:
                 s = n
-            nd, att = s, tuple(albedo[b])
-        elif kind[b] == 1:                         # metal, material.clj:21-28
+            return ("scatter", p, s, tuple(albedo[b]))
+        if kind[b] == 1:                           # metal, material.clj:21-28 / realm :147-158
             refl = reflect(d, n)
             refl = add(muls(random_unit_vec3(), fuzz[b]), refl)
             if not dot(refl, n) > 0:
-                return (0.0, 0.0, 0.0)
-            nd, att = refl, tuple(albedo[b])
-        else:                                      # dielectric, material.clj:34-46
-            ri = 1.0 / ior[b] if front else ior[b]
-            u = unit(d)
-            cos_theta = jmin1(dot(neg(u), n))
-            sin_theta = math.sqrt(1.0 - cos_theta * cos_theta)
-            refract_ok = ri * sin_theta <= 1.0
-            if not refract_ok:
-                do_reflect = True
-            else:                                  # `or` short-circuits: the draw happens only here
-                q = (1.0 - ri) / (1.0 + ri)
-                r0 = q * q
-                m = 1.0 - cos_theta
-                m2 = m * m
-                do_reflect = r0 + (1.0 - r0) * (m2 * m2 * m) > rand()
-            nd = reflect(u, n) if do_reflect else refract(u, n, ri)
-            att = (1.0, 1.0, 1.0)
-        return mulv(ray_color(p, nd, depth - 1), att)
+                return ("black",)
+            return ("scatter", p, refl, tuple(albedo[b]))
+        ri = 1.0 / ior[b] if front else ior[b]     # dielectric, material.clj:34-46 / realm :160-177
+        u = unit(d)
+        cos_theta = jmin1(dot(neg(u), n))
+        sin_theta = math.sqrt(1.0 - cos_theta * cos_theta)
+        if not ri * sin_theta <= 1.0:
+            do_reflect = True
+        elif realm:                                # realm/raytracing.clj:169-173: no Schlick, no draw
+            do_reflect = False
+        else:                                      # `or` short-circuits: the draw happens only here
+            q = (1.0 - ri) / (1.0 + ri)
+            r0 = q * q
+            m = 1.0 - cos_theta
+            m2 = m * m
+            do_reflect = r0 + (1.0 - r0) * (m2 * m2 * m) > rand()
+        return ("scatter", p, reflect(u, n) if do_reflect else refract(u, n, ri), (1.0, 1.0, 1.0))
+
+    def ray_color(o, d, depth):                    # main: recursive, innermost product first (:52-53)
+        r = bounce(o, d, depth)
+        if r[0] == "black":
+            return BLACK
+        if r[0] == "sky":
+            return r[1]
+        return mulv(ray_color(r[1], r[2], depth - 1), r[3])
+
+    def ray_color_realm(o, d):                     # realm/raytracing.clj:205-236: iterative, forward product
+        throughput, depth = (1.0, 1.0, 1.0), max_depth
+        while True:
+            r = bounce(o, d, depth)
+            if r[0] == "black":
+                return BLACK
+            if r[0] == "sky":
+                return mulv(throughput, r[1])
+            _, o, d, att = r
+            throughput = mulv(throughput, att)
+            depth -= 1
 
     W, H = cam.width, cam.height
     out = [[None] * W for _ in range(H)]
@@ -192,6 +216,9 @@ def render_main(soa, cam, spp, max_depth, seed=1):
                 else:                              # raytracing.clj:89-93
                     pd = random_in_unit_disk()
                     origin = add(add(cam.center, muls(cam.defocus_u, pd[0])), muls(cam.defocus_v, pd[1]))
-                acc = add(acc, ray_color(origin, sub(sample, origin), max_depth))
-            out[j][i] = divs(acc, spp)
+                if realm:
+                    acc = add(acc, ray_color_realm(origin, sub(sample, origin)))
+                else:
+                    acc = add(acc, ray_color(origin, sub(sample, origin), max_depth))
+            out[j][i] = muls(acc, 1.0 / spp) if realm else divs(acc, spp)
     return out, segments[0], st.blocks_drawn

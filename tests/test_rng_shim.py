@@ -43,10 +43,10 @@ def test_unit_vector_fields_and_schlick_word():
     assert got == want
 
 
-def _compare(world, cam, spp, depth, seed):
+def _compare(world, cam, spp, depth, seed, realm=False):
     soa = S.to_soa(world)
-    lin_o, _, st_o = O.render(soa, cam, spp, depth, seed=seed, flags=O.FLAGS_MAIN, threads=2)
-    lin_m, segs, _ = M.render_main(soa, cam, spp, depth, seed=seed)
+    lin_o, _, st_o = O.render(soa, cam, spp, depth, seed=seed, flags=O.FLAGS_REALM if realm else O.FLAGS_MAIN, threads=2)
+    lin_m, segs, _ = M.render_main(soa, cam, spp, depth, seed=seed, realm=realm)
     assert segs == st_o.segments
     assert np.array_equal(np.array(lin_m, dtype=np.float64), lin_o)
 
@@ -58,3 +58,9 @@ def test_sequential_reference_loop_reproduces_the_oracle_render():
     _compare(S.cover_hittables(7)[:40], CAM.main_camera(12, 7, **S.COVER_CAMERA), 2, 50, seed=5)
     # depth cap reached inside glass
     _compare(S.main_hittables(), CAM.main_camera(10), 2, 3, seed=2)
+
+
+def test_sequential_realm_loop_reproduces_the_oracle_render():
+    # realm semantics: forward product, no Schlick draw, no near-zero guard, no defocus, x (1/spp)
+    _compare(S.realm_hittables(), CAM.realm_camera(16), 3, 50, seed=1, realm=True)
+    _compare(S.cover_hittables(3)[:30], CAM.realm_camera(12), 2, 6, seed=4, realm=True)
