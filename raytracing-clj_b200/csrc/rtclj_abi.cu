@@ -420,6 +420,7 @@ static int download_rows(rtclj_ctx* c, const rtclj_camera* cam, int shard_index,
 
 namespace {
 std::mutex g_ctx_mu;
+std::mutex g_host_call_mu;  // the cached contexts are shared: one host-buffer call at a time
 std::vector<rtclj_ctx*> g_ctx_cache;  // one cached context per device for the host-buffer calls
 
 int cached_ctx(int device, rtclj_ctx** out) {
@@ -446,8 +447,7 @@ int rtclj_render_multi(const rtclj_scene* scene, const rtclj_camera* cam, const 
   rc = rtclj_device_count(&ndev);
   if (rc) return rc;
   if (ndev == 0) return fail(RTCLJ_E_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
-  static std::mutex render_mu;  // the cached contexts are shared: one host-buffer render at a time
-  std::lock_guard<std::mutex> lk(render_mu);
+  std::lock_guard<std::mutex> lk(g_host_call_mu);
 
   const size_t npix = (size_t)cam->width * (size_t)cam->height;
   std::vector<rtclj_ctx*> ctxs((size_t)n_devices);
@@ -502,6 +502,7 @@ int rtclj_render(const rtclj_scene* scene, const rtclj_camera* cam, const rtclj_
     if (!scene) return fail(RTCLJ_E_INVALID, "null scene");
     int rc = validate(cam, prm);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_host_call_mu);
     rtclj_ctx* c = nullptr;
     rc = cached_ctx(prm->device, &c);
     if (rc) return rc;
@@ -587,6 +588,7 @@ int rtclj_ctx_encode_ms(rtclj_ctx* c, double* count_scan_ms, double* write_ms) {
 int rtclj_encode_ppm_p3_gpu(int32_t device, const uint8_t* rgb8, int32_t width, int32_t height, char* out,
                             size_t capacity, size_t* len) {
   if (width <= 0 || height <= 0 || !len || !rgb8) return fail(RTCLJ_E_INVALID, "bad image or null len");
+  std::lock_guard<std::mutex> lk(g_host_call_mu);
   rtclj_ctx* c = nullptr;
   int rc = cached_ctx(device, &c);
   if (rc) return rc;

@@ -281,6 +281,36 @@ def test_device_resident_context_matches_host_call():
     ctx.close()
 
 
+def test_concurrent_host_calls_from_several_threads():
+    """JVM hosts call from pool threads (raytracing.clj:162-166): the host-buffer entry points share
+    one cached context per device and must serialise themselves."""
+    import threading
+    world, cam = S.main_hittables(), CAM.main_camera(64)
+    want = {seed: gpu(world, cam, 4, 50, seed=seed) for seed in (1, 2, 3, 4)}
+    got, errors = {}, []
+
+    def work(seed):
+        try:
+            for _ in range(3):
+                if seed % 2:
+                    got[seed] = gpu(world, cam, 4, 50, seed=seed)
+                else:  # the one-shard-per-call entry point, two shards
+                    lin = np.zeros((cam.height, cam.width, 3)); rgb = np.zeros((cam.height, cam.width, 3), dtype=np.uint8)
+                    for idx in range(2):
+                        gpu(world, cam, 4, 50, seed=seed, shard=(idx, 2, 3), out_linear=lin, out_rgb8=rgb)
+                    got[seed] = (lin, rgb, None)
+                render.encode_ppm(want[seed][1], device=0)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(s,)) for s in want]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for seed in want:
+        assert np.array_equal(got[seed][0], want[seed][0]) and np.array_equal(got[seed][1], want[seed][1])
+
+
 def test_error_behaviour():
     import ctypes as C
     cam = CAM.main_camera(16)
