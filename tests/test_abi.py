@@ -67,3 +67,20 @@ def test_argument_validation_without_compute():
     assert lib.rtclj_encode_ppm_p3(None, 0, 4, None, 0, C.byref(n)) == _abi.E_INVALID
     cam = _abi.Camera()
     assert lib.rtclj_camera_i(0, 10, C.byref(cam)) == _abi.E_INVALID
+
+
+def build_c_client(tmp_path):
+    """gcc -std=c11 -pedantic on a plain-C user of the header, linked against the library."""
+    import subprocess
+    libdir = os.path.join(ROOT, "raytracing-clj_b200")
+    exe = str(tmp_path / "abi_c_client")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    "-o", exe, os.path.join(ROOT, "tests", "native", "abi_c_client.c"),
+                    "-L", libdir, "-lrtclj_b200", "-Wl,-rpath," + libdir], check=True)
+    return exe
+
+
+def test_header_is_valid_c11_and_host_entry_points_work_from_c(tmp_path):
+    import subprocess
+    out = subprocess.run([build_c_client(tmp_path)], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == "ok host"

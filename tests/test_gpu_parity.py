@@ -311,6 +311,19 @@ def test_concurrent_host_calls_from_several_threads():
         assert np.array_equal(got[seed][0], want[seed][0]) and np.array_equal(got[seed][1], want[seed][1])
 
 
+def test_plain_c_client_renders_the_same_image(tmp_path):
+    """A C program (not Python) driving rtclj_render: the reference's scene, compared with the oracle."""
+    import subprocess
+    from test_abi import build_c_client
+    dump = str(tmp_path / "linear.f64")
+    out = subprocess.run([build_c_client(tmp_path), "gpu", dump], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == "ok gpu"
+    cam = CAM.main_camera(64, 36)
+    lin_o, _, _ = O.render(S.to_soa(S.main_hittables()), cam, 8, 50, seed=1, flags=O.FLAGS_MAIN, threads=4, samples_per_unit=8)
+    got = np.fromfile(dump, dtype=np.float64).reshape(36, 64, 3)
+    assert np.array_equal(got, lin_o)
+
+
 def test_error_behaviour():
     import ctypes as C
     cam = CAM.main_camera(16)
