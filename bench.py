@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(name="rtiow_cover_seed7_1920x1080_500spp_depth50", width=1920, height=1080, spp=500,
                 depth=50, scene_seed=7, render_seed=1)
-SHARD_ROWS = 4
+SHARD_ROWS = 1
 FLOP_PER_TEST, FLOP_PER_SEGMENT = 17, 5
 
 
