@@ -252,6 +252,29 @@ def test_full_size_properties_config2():
     assert np.array_equal(rgb_o[rows[0]:rows[1]], rgb[rows[0]:rows[1]])
 
 
+def test_extreme_image_shapes():
+    """Maximum sizes the reference could be asked for: a 7680x4320 frame (33 M pixels), one-pixel-wide
+    and one-pixel-high images, and a small image at 4000 spp (chunked sums).  Rows / whole images
+    against the oracle."""
+    world = S.main_hittables()
+    cam = CAM.main_camera(7680, 4320)
+    lin, rgb, st = gpu(world, cam, 1, 6, seed=3)
+    assert st["samples"] == 7680 * 4320 and st["samples_per_unit"] == 1
+    for j in (0, 2161, 4319):
+        lin_o, rgb_o, _ = O.render(S.to_soa(world), cam, 1, 6, seed=3, flags=O.FLAGS_MAIN, threads=8, rows=(j, j + 1))
+        assert np.array_equal(lin_o[j], lin[j]) and np.array_equal(rgb_o[j], rgb[j])
+    assert render.encode_ppm(rgb, device=0) == render.encode_ppm(rgb)      # 33 M lines of text, both writers
+    del lin, rgb
+    assert_same(world, CAM.main_camera(1, 300), 6, 50, 4, O.FLAGS_MAIN)
+    assert_same(world, CAM.main_camera(700, 1), 6, 50, 5, O.FLAGS_MAIN)
+    soa = S.to_soa(world)
+    small = CAM.main_camera(12, 7)
+    lin_g, rgb_g, st_g = gpu(soa, small, 4000, 50, seed=6)
+    lin_o, rgb_o, st_o = O.render(soa, small, 4000, 50, seed=6, flags=O.FLAGS_MAIN, threads=8,
+                                  samples_per_unit=st_g["samples_per_unit"])
+    assert np.array_equal(lin_o, lin_g) and np.array_equal(rgb_o, rgb_g) and st_g["segments"] == st_o.segments
+
+
 def test_multi_device_equals_single_device():
     import ctypes as C
     n = C.c_int()
