@@ -309,7 +309,7 @@ def main():
         "config": {"workload": WORKLOAD["name"], "n_spheres": n, "samples_per_step": W * H * spp,
                    "segments_per_step": segs_per_step, "samples_per_sec": W * H * spp * args.steps / (total_ms * 1e-3),
                    "parallelism": f"rows interleaved over {world_size} GPU(s), tiles of {SHARD_ROWS} rows",
-                   "l2": "flushed between timed steps (256 MiB write); the scene lives in shared memory",
+                   "l2": "flushed between timed steps (256 MiB write); the sphere table lives on chip (constant cache)",
                    "rgb8_checksum": checksum},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": lin_bytes + rgb_bytes, "ms_per_step": 1e3 * float(e2e_t.sum().item()) / e2e_steps},
