@@ -20,7 +20,8 @@
  *                           realm/raytracing.clj:350-358 (host)
  *   rtclj_ctx_encode_ppm_p3, rtclj_encode_ppm_p3_gpu
  *                           the same writer as device kernels (device / host buffers)
- *   rtclj_encode_png        ppm->png, src/raytracing.clj:176 (src/ppm2png.clj:35-87)
+ *   rtclj_encode_png, rtclj_decode_ppm_p3
+ *                           ppm->png, src/raytracing.clj:176 (src/ppm2png.clj:35-87): writer, reader
  *   rtclj_camera_main/_realm/_i
  *                           the camera let-blocks, src/raytracing.clj:105-139 ;
  *                           realm/raytracing.clj:264-280,306-322 ;
@@ -211,6 +212,14 @@ int rtclj_encode_ppm_p3_gpu(int32_t device, const uint8_t *rgb8, int32_t width, 
  * blocks.  Call with out == NULL to get the required capacity in *len. */
 int rtclj_encode_png(const uint8_t *rgb8, int32_t width, int32_t height, uint8_t *out, size_t capacity,
                      size_t *len);
+
+/* The reader half of ppm->png (src/ppm2png.clj:35-87 reads "P3", "W H", a maximum <= 255 and one
+ * "r g b" line per pixel; this parser accepts any whitespace between the tokens).  Call with
+ * out_rgb8 == NULL to get the dimensions; RTCLJ_E_INVALID for a malformed file (bad magic, bad
+ * dimensions, maximum outside 0..255, a component outside 0..max, too few or too many values),
+ * RTCLJ_E_BUFFER if capacity < 3*W*H. */
+int rtclj_decode_ppm_p3(const char *text, size_t len, int32_t *width, int32_t *height,
+                        uint8_t *out_rgb8, size_t capacity);
 
 /* Clojure's Ratio -> double (Ratio.doubleValue rounds through 16 decimal digits). */
 double rtclj_ratio_to_double(int64_t num, int64_t den);

@@ -72,6 +72,8 @@ SYMBOLS = {
     "rtclj_ctx_encode_ppm_p3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                           C.POINTER(C.c_size_t), C.c_void_p]),
     "rtclj_ctx_encode_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "rtclj_decode_ppm_p3": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p,
+                                      C.c_size_t]),
     "rtclj_encode_png": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_size_t)]),
     "rtclj_ratio_to_double": (C.c_double, [C.c_int64, C.c_int64]),

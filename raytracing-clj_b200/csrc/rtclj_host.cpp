@@ -215,6 +215,42 @@ int rtclj_encode_png(const uint8_t* rgb8, int32_t width, int32_t height, uint8_t
   return RTCLJ_OK;
 }
 
+// ---- P3 reader (the input side of ppm->png): whitespace-separated decimal tokens
+int rtclj_decode_ppm_p3(const char* text, size_t len, int32_t* width, int32_t* height, uint8_t* out_rgb8,
+                        size_t capacity) {
+  if (!text || !width || !height) return RTCLJ_E_INVALID;
+  size_t pos = 0;
+  auto skip_ws = [&]() { while (pos < len && (text[pos] == ' ' || text[pos] == '\n' || text[pos] == '\r' || text[pos] == '\t')) ++pos; };
+  auto number = [&](long long& v) -> bool {  // one non-negative decimal token
+    skip_ws();
+    if (pos >= len || text[pos] < '0' || text[pos] > '9') return false;
+    v = 0;
+    while (pos < len && text[pos] >= '0' && text[pos] <= '9') {
+      v = v * 10 + (text[pos++] - '0');
+      if (v > 0x7fffffffLL) return false;
+    }
+    return pos >= len || text[pos] == ' ' || text[pos] == '\n' || text[pos] == '\r' || text[pos] == '\t';
+  };
+  skip_ws();
+  if (pos + 2 > len || text[pos] != 'P' || text[pos + 1] != '3') return RTCLJ_E_INVALID;
+  pos += 2;
+  long long w = 0, h = 0, maxv = 0;
+  if (!number(w) || !number(h) || !number(maxv)) return RTCLJ_E_INVALID;
+  if (w <= 0 || h <= 0 || maxv > 255) return RTCLJ_E_INVALID;
+  *width = (int32_t)w;
+  *height = (int32_t)h;
+  if (!out_rgb8) return RTCLJ_OK;
+  const size_t n = (size_t)w * (size_t)h * 3;
+  if (capacity < n) return RTCLJ_E_BUFFER;
+  for (size_t i = 0; i < n; ++i) {
+    long long v = 0;
+    if (!number(v) || v > maxv) return RTCLJ_E_INVALID;
+    out_rgb8[i] = (uint8_t)v;
+  }
+  skip_ws();
+  return pos == len ? RTCLJ_OK : RTCLJ_E_INVALID;  // trailing garbage / more values than W*H
+}
+
 // clojure.lang.Ratio.doubleValue: BigDecimal(num).divide(BigDecimal(den), DECIMAL64).doubleValue(),
 // i.e. the quotient rounded HALF_EVEN to 16 significant decimal digits, then to double
 // (SURVEY.md Appendix B.1).  Integral quotients are Longs in Clojure and stay exact.

@@ -181,6 +181,24 @@ def encode_png(rgb8: np.ndarray) -> bytes:
     return _two_call(_abi.lib().rtclj_encode_png, img)
 
 
+def decode_ppm(text: bytes) -> np.ndarray:
+    """The reader half of `ppm->png` (ppm2png.clj:35-87): P3 text -> uint8 [H,W,3]."""
+    lib = _abi.lib()
+    w, h = C.c_int32(), C.c_int32()
+    _abi.check(lib.rtclj_decode_ppm_p3(text, len(text), C.byref(w), C.byref(h), None, 0))
+    out = np.zeros((h.value, w.value, 3), dtype=np.uint8)
+    _abi.check(lib.rtclj_decode_ppm_p3(text, len(text), C.byref(w), C.byref(h), out.ctypes.data, out.size))
+    return out
+
+
+def ppm_to_png(source: str, dest: str) -> None:
+    """`(ppm->png source dest)`, raytracing.clj:176."""
+    with open(source, "rb") as f:
+        rgb8 = decode_ppm(f.read())
+    write_png(dest, rgb8)
+    print(f"Processed {source} into {dest}")
+
+
 def write_png(path: str, rgb8: np.ndarray) -> None:
     with open(path, "wb") as f:
         f.write(encode_png(rgb8))

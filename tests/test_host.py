@@ -5,6 +5,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import pytest
 
 import oracle_lib as O
 import raytracing_clj_b200 as R
@@ -122,6 +123,28 @@ def test_ppm_of_reference_golden_round_trips():
     text = render.encode_ppm(gold).decode().split("\n")
     assert text[1] == "400 225" and text[3] == "175 198 0"   # first pixel of the reference's scene.ppm
     assert len(text) == 90003 + 1                              # 90 003 lines
+
+
+def test_ppm_reader_round_trip_and_rejections(tmp_path):
+    """The reader half of ppm->png (ppm2png.clj:35-87): our own P3 text back to the pixels, the
+    reference's committed render, and the malformed inputs the reference rejects."""
+    import io
+    from PIL import Image
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, size=(9, 13, 3), dtype=np.uint8)
+    assert np.array_equal(render.decode_ppm(render.encode_ppm(img)), img)
+    assert np.array_equal(render.decode_ppm(b"P3 2 1 255 1 2 3\t4 5 6"), np.array([[[1, 2, 3], [4, 5, 6]]], dtype=np.uint8))
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_images.npz"))["scene_main"]
+    assert np.array_equal(render.decode_ppm(render.encode_ppm(gold)), gold)
+    for bad in (b"P6\n1 1\n255\n0 0 0\n", b"P3\n1\n", b"P3\n1 1\n256\n0 0 0\n", b"P3\n1 1\n255\n0 0\n",
+                b"P3\n1 1\n255\n0 0 0 0\n", b"P3\n1 1\n255\n0 0 300\n", b"P3\n1 1\n255\n0 x 0\n", b"P3\n0 1\n255\n",
+                b"P3\n1 1\n100\n0 0 101\n"):
+        with pytest.raises(_abi.RtcljError):
+            render.decode_ppm(bad)
+    src, dst = str(tmp_path / "scene.ppm"), str(tmp_path / "scene.png")
+    render.write_ppm(src, gold)
+    render.ppm_to_png(src, dst)                                   # (ppm->png "scene.ppm" "scene.png"), raytracing.clj:176
+    assert np.array_equal(np.asarray(Image.open(dst).convert("RGB")), gold)
 
 
 def test_png_encoder_decodes_to_the_same_pixels():
