@@ -21,7 +21,7 @@ def main_variant(spp: int = 100, depth: int = 50, out: str = "scene.ppm", seed: 
     _, rgb8, st = render.render(scenes.main_hittables(), camera.main_camera(), spp, depth, seed=seed,
                                 flags=_abi.FLAGS_MAIN, want_linear=False)
     render.write_ppm(out, rgb8)
-    render.write_png(out[:-4] + ".png" if out.endswith(".ppm") else out + ".png", rgb8)  # ppm->png, raytracing.clj:176
+    render.ppm_to_png(out, out[:-4] + ".png" if out.endswith(".ppm") else out + ".png")  # (ppm->png "scene.ppm" "scene.png"), raytracing.clj:176
     print(f'"Elapsed time: {1e3 * (time.perf_counter() - t0):.3f} msecs"  ({st["segments"]} ray segments)')
     return st
 
