@@ -347,6 +347,22 @@ def test_plain_c_client_renders_the_same_image(tmp_path):
     assert np.array_equal(got, lin_o)
 
 
+def test_entry_points_write_the_files_the_reference_writes(tmp_path, monkeypatch):
+    """`clojure -M:main 8 50` / `-M:realm` / raytracing-i: scene.ppm + scene.png, scene-realm.ppm, scene-i.ppm."""
+    from PIL import Image
+    from raytracing_clj_b200 import main as entry
+    monkeypatch.chdir(tmp_path)
+    st = entry.main_variant(8, 50)
+    ppm = render.decode_ppm(open("scene.ppm", "rb").read())
+    assert ppm.shape == (225, 400, 3) and st["samples"] == 400 * 225 * 8
+    assert np.array_equal(np.asarray(Image.open("scene.png").convert("RGB")), ppm)
+    _, rgb_o, _ = O.render(S.to_soa(S.main_hittables()), CAM.main_camera(), 8, 50, seed=1, flags=O.FLAGS_MAIN, threads=8,
+                           samples_per_unit=st["samples_per_unit"])
+    assert np.array_equal(ppm, rgb_o)
+    entry.i_variant()
+    assert render.decode_ppm(open("scene-i.ppm", "rb").read()).shape == (224, 400, 3)
+
+
 def test_error_behaviour():
     import ctypes as C
     cam = CAM.main_camera(16)
