@@ -85,7 +85,11 @@ enum {
 
 /* The hittable list as a structure of arrays, in LIST ORDER (the first body wins an
  * exact tie, raytracing.clj:33-43).  Replaces `to-render` (raytracing.clj:102) and the
- * Entity[] (realm/raytracing.clj:285-301). */
+ * Entity[] (realm/raytracing.clj:285-301).
+ * Accepted values: everything the reference's constructors accept (negative or zero radius,
+ * fuzz > 1, any ior, albedo outside [0,1]) as long as it is finite and |coordinate|, |radius| < 1e18;
+ * NaN / infinity / larger magnitudes return RTCLJ_E_INVALID (the reference's scan degenerates on a NaN
+ * root, and the fp32 cull squares coordinates).  Spheres beyond 1e15 are simply never culled. */
 typedef struct rtclj_scene {
   int32_t n;
   int32_t _pad;

@@ -128,6 +128,16 @@ int auto_samples_per_unit(int W, int H, int spp) {
 int validate(const rtclj_camera* cam, const rtclj_params* prm) {
   if (!cam || !prm) return fail(RTCLJ_E_INVALID, "null camera or params");
   if (cam->width <= 0 || cam->height <= 0) return fail(RTCLJ_E_INVALID, "image size must be positive");
+  {
+    bool finite = std::isfinite(cam->defocus_angle);
+    for (int a = 0; a < 3; ++a)
+      finite = finite && std::isfinite(cam->pixel00[a]) && std::isfinite(cam->pixel_du[a]) && std::isfinite(cam->pixel_dv[a]) &&
+               std::isfinite(cam->center[a]) && std::isfinite(cam->defocus_u[a]) && std::isfinite(cam->defocus_v[a]);
+    if (!finite) return fail(RTCLJ_E_INVALID, "non-finite camera value");
+    for (int a = 0; a < 3; ++a)
+      if (!(std::fabs(cam->center[a]) + std::fabs(cam->defocus_u[a]) + std::fabs(cam->defocus_v[a]) < 1e18))
+        return fail(RTCLJ_E_INVALID, "camera coordinates beyond 1e18 are not supported");
+  }
   if ((uint64_t)cam->width * (uint64_t)cam->height > 0xffffffffull)
     return fail(RTCLJ_E_INVALID, "more than 2^32 pixels");
   if (prm->spp <= 0) return fail(RTCLJ_E_INVALID, "spp must be positive");
@@ -244,6 +254,15 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
     const int k = s->material[i];
     if (k != RTCLJ_LAMBERTIAN && k != RTCLJ_METAL && k != RTCLJ_DIELECTRIC)
       return fail(RTCLJ_E_INVALID, "sphere %d: unknown material id %d", i, k);
+    // NaN / infinity: the reference's sequential scan degenerates (a NaN root is "accepted" and every
+    // later body then wins); that is garbage in either implementation, so it is refused here
+    bool finite = std::isfinite(s->radius[i]) && std::isfinite(s->fuzz[i]) && std::isfinite(s->ior[i]);
+    for (int a = 0; a < 3; ++a) finite = finite && std::isfinite(s->center_xyz[3 * i + a]) && std::isfinite(s->albedo_rgb[3 * i + a]);
+    if (!finite) return fail(RTCLJ_E_INVALID, "sphere %d: non-finite parameter", i);
+    // the fp32 cull squares coordinates of ray origins, which lie on sphere surfaces: keep them below 1e18
+    double reach = std::fabs(s->radius[i]);
+    for (int a = 0; a < 3; ++a) reach = std::max(reach, std::fabs(s->center_xyz[3 * i + a]));
+    if (!(reach < 1e18)) return fail(RTCLJ_E_INVALID, "sphere %d: coordinates beyond 1e18 are not supported", i);
   }
   CU(cudaSetDevice(c->device));
 
@@ -281,11 +300,19 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
       }
       m.pad = 0;
       mats[(size_t)i] = m;
-      cx = (float)(C[0] - shift[0]); cy = (float)(C[1] - shift[1]); cz = (float)(C[2] - shift[2]);
-      // Ws = r^2 (1 + 8 eps) - |c|^2 (1 - 96 eps), c = the fp32-rounded shifted centre; rounded UP
-      const double eps = (double)kEps32;
-      const double c2 = (double)cx * cx + (double)cy * cy + (double)cz * cz;
-      r2s = round_up_to_float(r * r * (1.0 + 8.0 * eps) - c2 * (1.0 - 96.0 * eps));
+      const double far = std::max(std::max(std::fabs(C[0] - shift[0]), std::fabs(C[1] - shift[1])),
+                                  std::max(std::fabs(C[2] - shift[2]), std::fabs(r)));
+      if (far < 1e15) {
+        cx = (float)(C[0] - shift[0]); cy = (float)(C[1] - shift[1]); cz = (float)(C[2] - shift[2]);
+        // Ws = r^2 (1 + 8 eps) - |c|^2 (1 - 96 eps), c = the fp32-rounded shifted centre; rounded UP
+        const double eps = (double)kEps32;
+        const double c2 = (double)cx * cx + (double)cy * cy + (double)cz * cz;
+        r2s = round_up_to_float(r * r * (1.0 + 8.0 * eps) - c2 * (1.0 - 96.0 * eps));
+      } else {
+        // squares beyond the fp32 range: the sphere is never culled (c = 0, Ws huge) and never
+        // dropped by the fp32 prefilter; the fp64 test decides
+        r2s = 3.0e38f;
+      }
     }
     // pair-packed: pair p = i/2, half h = i&1 -> {cx[h], cy[2+h]} in vec0, {cz[h], r2s[2+h]} in vec1
     const int p = i >> 1, h = i & 1;

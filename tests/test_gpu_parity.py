@@ -140,6 +140,16 @@ def test_far_origin_and_huge_spheres():
     cam = CAM.main_camera(96, 54, vfov=40.0, look_from=(600.0, 30.0, 400.0), look_at=(0.0, 0.0, 0.0),
                           defocus_angle=0.0, focus_dist=10.0)
     assert_same(world, cam, 8, 50, 13, O.FLAGS_MAIN)
+    # coordinates whose squares leave the fp32 range: such spheres are never culled, such origins scan everything
+    sp, mat = R.hittable.sphere, R.material
+    giant_ground = S.cover_hittables(5)[1:60] + [S.body(sp((0.0, -2e15 - 0.5, 0.0), 2e15), mat.lambertian((0.5, 0.6, 0.5))),
+                                                 S.body(sp((4e16, 3e16, -9e16), 2e16), mat.metal((0.9, 0.9, 0.9), 0.0))]
+    assert_same(giant_ground, CAM.main_camera(64, 36, **S.COVER_CAMERA), 8, 50, 14, O.FLAGS_MAIN)
+    planet = [S.body(sp((0.0, 0.0, 0.0), 1e15), mat.lambertian((0.3, 0.5, 0.8))),
+              S.body(sp((1.2e15, 0.0, 0.0), 1e14), mat.dielectric(1.5))]
+    far_cam = CAM.main_camera(48, 27, vfov=60.0, look_from=(4e15, 1e15, 2e15), look_at=(0.0, 0.0, 0.0),
+                              defocus_angle=0.0, focus_dist=10.0)
+    assert_same(planet, far_cam, 8, 50, 15, O.FLAGS_MAIN)
 
 
 def test_primary_ray_4k_bit_exact_8bit():
@@ -361,6 +371,22 @@ def test_entry_points_write_the_files_the_reference_writes(tmp_path, monkeypatch
     assert np.array_equal(ppm, rgb_o)
     entry.i_variant()
     assert render.decode_ppm(open("scene-i.ppm", "rb").read()).shape == (224, 400, 3)
+
+
+def test_non_finite_inputs_are_refused():
+    world = S.main_hittables()
+    for field, value in (("hittable/center", (float("nan"), 0.0, -1.0)), ("hittable/radius", float("inf")),
+                         ("material/albedo", (0.5, float("nan"), 0.5))):
+        bad = [dict(b) for b in world]
+        bad[1][field] = value
+        with pytest.raises(_abi.RtcljError) as e:
+            gpu(bad, CAM.main_camera(16), 1, 5)
+        assert e.value.code == _abi.E_INVALID
+    import dataclasses
+    cam = dataclasses.replace(CAM.main_camera(16), center=(float("inf"), 0.0, 0.0))
+    with pytest.raises(_abi.RtcljError) as e:
+        gpu(world, cam, 1, 5)
+    assert e.value.code == _abi.E_INVALID
 
 
 def test_error_behaviour():
