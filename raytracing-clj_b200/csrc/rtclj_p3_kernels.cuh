@@ -9,8 +9,10 @@
 //   1. text bytes of the whole run (one pass over its pixels)           -> state[2 + b]
 //   2. start of the run = header + the counts of all CTAs before it     (spin on their words; a CTA
 //      only ever waits for CTAs that took an earlier ticket, so the wait cannot deadlock)
-//   3. per tile: thread offsets by a CTA scan, decimal text packed into 32-bit words in registers,
-//      staged in shared memory at the alignment of its destination, written with 16-byte stores.
+//   3. per tile: thread offsets by a CTA scan; digits for two values at a time in 16-bit lanes, a pixel's
+//      three fields concatenated into its 6..12 bytes in registers, shifted to the stream's byte phase
+//      and stored as whole words; staged in shared memory at the alignment of its destination, written
+//      with 16-byte stores.
 //      The pixels come from L2 the second time (an image is far smaller than the 126 MB L2).
 // count_only stops after step 2 (sizing calls, and callers whose buffer is below the worst case).
 #pragma once
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(kP3Threads) p3_encode_kernel(const unsigned ch
                                                                size_t ntiles, size_t tiles_per_cta,
                                                                unsigned long long* __restrict__ state,
                                                                unsigned char* __restrict__ out, P3Header hdr, int count_only) {
-  __shared__ __align__(16) unsigned char stage[kP3StageBytes + 16];  // + the junk word of the branch-free writer
+  __shared__ __align__(16) unsigned char stage[kP3StageBytes];
   __shared__ unsigned long long red[kP3Threads / 32];
   __shared__ unsigned wsum[kP3Threads / 32];
   __shared__ unsigned cta_s;
@@ -152,46 +154,46 @@ __global__ void __launch_bounds__(kP3Threads) p3_encode_kernel(const unsigned ch
     }
     unsigned char* dst = out + g;
     const unsigned shift = (unsigned)(reinterpret_cast<uintptr_t>(dst) & 15u);
-    {
-      // Branch-free: every value is appended (padding values append nothing), a word is stored after
-      // every value -- to the junk word unless the accumulator filled.  The thread's first word may
-      // hold bytes of the previous thread and its last word bytes of the next: those two are merged
-      // with atomicOr into the zeroed stage, the words in between are plain stores.
+    if (n > 0) {
+      // Pixel by pixel: the three fields of a pixel are concatenated into its 6..12 bytes of text
+      // (three words), which are shifted to the stream's byte phase and stored.  A pixel is at least
+      // six bytes, so every pixel completes at least one word: the thread's first word (which may hold
+      // bytes of the previous thread) is always the first word of its first pixel, and its last,
+      // partial word may hold bytes of the next thread -- those two are merged with atomicOr into the
+      // zeroed stage, everything in between is plain predicated stores.  No per-value bookkeeping.
       uint32_t* stage32 = reinterpret_cast<uint32_t*>(stage);
       const unsigned s0 = shift + offset;
-      const unsigned widx0 = s0 >> 2;
-      unsigned widx = widx0;
-      uint32_t firstword = 0u;
-      P3Acc acc;
-      acc.fill8 = 8u * (s0 & 3u);
+      unsigned widx = s0 >> 2;
+      uint32_t lo = 0u, fill8 = 8u * (s0 & 3u);
+      uint32_t drop[3];
+      P3Digits2 even[3], odd[3];
 #pragma unroll
       for (int wi = 0; wi < 3; ++wi) {
-        uint32_t drop = 0x10101010u - (p3_extra_digits4(w[wi]) << 3);  // per value: 8 * leading zeros dropped
-        if (n < kP3PixPerThread) drop += p3_padding_lanes(wi, n);
-        const P3Digits2 even = p3_digits2(w[wi] & 0x00ff00ffu), odd = p3_digits2((w[wi] >> 8) & 0x00ff00ffu);
+        drop[wi] = 0x10101010u - (p3_extra_digits4(w[wi]) << 3);  // per value: 8 * leading zeros dropped
+        even[wi] = p3_digits2(w[wi] & 0x00ff00ffu);
+        odd[wi] = p3_digits2((w[wi] >> 8) & 0x00ff00ffu);
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = 4 * wi + j;
-          const uint32_t field = p3_field((j & 1) ? odd : even, j >> 1, (k % 3 == 2) ? 0x0au : 0x20u);
-          p3_acc_append(acc, field, p3_byte_perm(drop, 0u, 0x4440u + (unsigned)j));
-          const bool full = p3_acc_full(acc);
-          const bool is_first = full && widx == widx0;
-          const uint32_t word = acc.lo;
-          firstword = is_first ? word : firstword;
-          stage32[(full && !is_first) ? widx : (unsigned)(kP3StageBytes / 4)] = word;
-          widx += full ? 1u : 0u;
-          acc.lo = full ? acc.hi : acc.lo;
-          acc.fill8 -= full ? 32u : 0u;
+      for (int px = 0; px < kP3PixPerThread; ++px) {
+        if (px < n) {
+          uint32_t f[3], d[3];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const int k = 3 * px + ch, wi = k >> 2, j = k & 3;  // value k sits in byte j of word wi
+            f[ch] = p3_field((j & 1) ? odd[wi] : even[wi], j >> 1, ch == 2 ? 0x0au : 0x20u);
+            d[ch] = p3_byte_perm(drop[wi], 0u, 0x4440u + (unsigned)j);
+          }
+          const P3Pixel pix = p3_pixel_text(f[0], f[1], f[2], d[0], d[1], d[2]);
+          const P3Append ap = p3_append_pixel(lo, fill8, pix);
+          if (px == 0) atomicOr(stage32 + widx, ap.out0); else stage32[widx] = ap.out0;
+          if (ap.nfull >= 2u) stage32[widx + 1] = ap.out1;
+          if (ap.nfull == 3u) stage32[widx + 2] = ap.out2;
+          widx += ap.nfull;
+          lo = ap.lo;
+          fill8 = ap.fill8;
         }
       }
-      if (n > 0) {
-        if (widx != widx0) {
-          atomicOr(stage32 + widx0, firstword);
-          if (acc.fill8) atomicOr(stage32 + widx, acc.lo);
-        } else if (acc.fill8) {
-          atomicOr(stage32 + widx, acc.lo);  // (cannot happen for n >= 1: a pixel is at least 6 bytes)
-        }
-      }
+      if (fill8) atomicOr(stage32 + widx, lo);
     }
     __syncthreads();
     // stage[shift .. shift+total) -> dst[0 .. total): whole 16-byte chunks as vectors, the two ends

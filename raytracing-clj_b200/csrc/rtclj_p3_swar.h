@@ -61,38 +61,58 @@ RTCLJ_HD uint32_t p3_field(const P3Digits2& d, int lane, uint32_t sep) {
   return f + (0x00303030u | (sep << 24));
 }
 
-// Little-endian byte accumulator: appends the text of one value (its field with the leading
-// zero digits dropped) and reports whether a whole 32-bit word is ready.
-struct P3Acc {
-  uint32_t lo = 0, hi = 0;
-  uint32_t fill8 = 0;  // valid bits in lo (0, 8, 16 or 24 between appends)
-};
-// drop8 = 8 * (number of leading zero digits to drop) = 16 - 8 * (digits - 1); drop8 = 32 appends nothing
-// (the padding values of a partial thread).
-RTCLJ_HD void p3_acc_append(P3Acc& a, uint32_t field, uint32_t drop8) {
+// ---- shifts that are defined for the whole range 0..32 (C++ leaves x << 32 undefined; PTX does not)
+RTCLJ_HD uint32_t p3_shl(uint32_t x, uint32_t s) {   // x << s, 0 for s = 32
 #ifdef __CUDA_ARCH__
-  const uint32_t c = __funnelshift_rc(field, 0u, drop8);  // field >> drop8, 0 for drop8 = 32
-  a.hi = __funnelshift_l(c, 0u, a.fill8);                 // the bits of c that do not fit in lo (0 when fill8 == 0)
+  return __funnelshift_lc(0u, x, s);
 #else
-  const uint32_t c = drop8 >= 32u ? 0u : field >> drop8;
-  a.hi = a.fill8 ? c >> (32u - a.fill8) : 0u;
+  return s >= 32u ? 0u : x << s;
 #endif
-  a.lo |= c << a.fill8;
-  a.fill8 += 32u - drop8;
 }
-RTCLJ_HD bool p3_acc_full(const P3Acc& a) { return a.fill8 >= 32u; }
-RTCLJ_HD uint32_t p3_acc_pop(P3Acc& a) {
-  const uint32_t w = a.lo;
-  a.lo = a.hi; a.hi = 0u; a.fill8 -= 32u;
-  return w;
+RTCLJ_HD uint32_t p3_shr(uint32_t x, uint32_t s) {   // x >> s, 0 for s = 32
+#ifdef __CUDA_ARCH__
+  return __funnelshift_rc(x, 0u, s);
+#else
+  return s >= 32u ? 0u : x >> s;
+#endif
 }
-// Per byte lane: 16 where the value at that position of word `wi` lies beyond the thread's n pixels
-// (added to the drop lanes, it turns their 16 into the "append nothing" 32).
-RTCLJ_HD uint32_t p3_padding_lanes(int wi, int n) {
-  uint32_t m = 0;
-  for (int j = 0; j < 4; ++j)
-    if (4 * wi + j >= 3 * n) m |= 0x10u << (8 * j);
-  return m;
+RTCLJ_HD uint32_t p3_funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {  // high word of (hi:lo) << s, s in 0..31
+#ifdef __CUDA_ARCH__
+  return __funnelshift_l(lo, hi, s);
+#else
+  return s ? (hi << s) | (lo >> (32u - s)) : hi;
+#endif
+}
+
+// The text of one pixel, "r g b\n", as 6..12 little-endian bytes in three words.
+// f0..f2: the 4-byte fields of its values (p3_field), d0..d2: 8 * (leading zero digits to drop).
+struct P3Pixel { uint32_t w0, w1, w2, bits; };
+RTCLJ_HD P3Pixel p3_pixel_text(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t d0, uint32_t d1, uint32_t d2) {
+  const uint32_t c0 = f0 >> d0, c1 = f1 >> d1, c2 = f2 >> d2;   // d <= 16
+  const uint32_t n0 = 32u - d0, n01 = n0 + (32u - d1);          // bits of r; of r and g (32..64)
+  P3Pixel p;
+  p.w0 = c0 | p3_shl(c1, n0);
+  p.w1 = (c1 >> (32u - n0)) | p3_shl(c2, n01 - 32u);
+  p.w2 = p3_shr(c2, 64u - n01);
+  p.bits = n01 + (32u - d2);
+  return p;
+}
+
+// Appends a pixel to a byte stream whose pending word `lo` holds fill8 (0, 8, 16, 24) valid bits.
+// A pixel is at least 48 bits, so out[0] is always a complete word; nfull (1..3) words are complete.
+struct P3Append { uint32_t out0, out1, out2, nfull, lo, fill8; };
+RTCLJ_HD P3Append p3_append_pixel(uint32_t lo, uint32_t fill8, const P3Pixel& p) {
+  const uint32_t t0 = lo | (p.w0 << fill8);
+  const uint32_t t1 = p3_funnel_l(p.w0, p.w1, fill8);
+  const uint32_t t2 = p3_funnel_l(p.w1, p.w2, fill8);
+  const uint32_t t3 = p3_funnel_l(p.w2, 0u, fill8);
+  const uint32_t total = fill8 + p.bits;   // 48..120
+  P3Append a;
+  a.out0 = t0; a.out1 = t1; a.out2 = t2;
+  a.nfull = total >> 5;
+  a.lo = a.nfull == 1u ? t1 : (a.nfull == 2u ? t2 : t3);
+  a.fill8 = total & 31u;
+  return a;
 }
 
 }  // namespace rtclj
