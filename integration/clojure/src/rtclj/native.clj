@@ -97,3 +97,30 @@
         (aset realm (+ 1 (* 3 p)) (aget c 1))
         (aset realm (+ 2 (* 3 p)) (aget c 2))))
     realm))
+
+;; int rtclj_encode_ppm_p3_gpu(int32_t device, const uint8_t* rgb8, int32_t width, int32_t height,
+;;                             char* out, size_t capacity, size_t* len)
+(def ^:private rtclj-encode-ppm-p3-gpu
+  (downcall "rtclj_encode_ppm_p3_gpu"
+            (FunctionDescriptor/of ValueLayout/JAVA_INT
+                                   (into-array MemoryLayout
+                                               [ValueLayout/JAVA_INT ValueLayout/ADDRESS ValueLayout/JAVA_INT ValueLayout/JAVA_INT
+                                                ValueLayout/ADDRESS ValueLayout/JAVA_LONG ValueLayout/ADDRESS]))))
+
+(defn write-ppm!
+  "The write-color! loop (raytracing.clj:172-175) as ONE call: rgb8 is a byte[] of W*H*3 gamma-encoded
+   components (what write-color! computes per pixel; rtclj_render fills it when asked for out_rgb8);
+   the P3 text is produced by the device kernels and handed to a single .write."
+  [^String path ^bytes rgb8 width height & {:keys [device] :or {device 0}}]
+  (with-open [a (Arena/ofConfined)]
+    (let [w     (int width) h (int height)
+          src   (.allocateFrom a ValueLayout/JAVA_BYTE rgb8)
+          cap   (+ 64 (* 12 (long w) (long h)))            ; "255 255 255\n" per pixel + header
+          out   (.allocate a cap 16)
+          len   (.allocate a 8 8)
+          rc    (int (.invokeWithArguments rtclj-encode-ppm-p3-gpu [(int device) src w h out cap len]))]
+      (when-not (zero? rc)
+        (throw (ex-info (last-error) {:rtclj/code rc})))
+      (let [n (.get len ValueLayout/JAVA_LONG 0)]
+        (with-open [o (java.io.FileOutputStream. path)]
+          (.write (.getChannel o) (.asByteBuffer (.asSlice out 0 n))))))))
