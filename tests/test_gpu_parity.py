@@ -101,6 +101,42 @@ def test_cull_equals_exhaustive_fp64_scan():
     assert sb["exact_tests"] == sb["segments"] * len(world)
 
 
+def test_cull_fuzz_against_exhaustive_scan():
+    """The conservative fp32 cull + prefilter against the exhaustive fp64 scan on random scenes at
+    scales from 1e-3 to 1e9, cameras inside, near and far, grazing rays, tiny and huge radii, clustered
+    and coincident centres -- both kernels.  One missed sphere anywhere changes the image."""
+    rng = np.random.default_rng(20261018)
+    sp, mat = R.hittable.sphere, R.material
+    for case in range(int(os.environ.get("RTCLJ_FUZZ_CASES", "48"))):   # a long soak: RTCLJ_FUZZ_CASES=1500
+        scale = 10.0 ** rng.uniform(-3, 9)
+        n = int(rng.choice([1, 2, 7, 31, 64, 200, 513]))
+        spread = scale * 10.0 ** rng.uniform(-2, 2)
+        offset = rng.normal(size=3) * scale * (0 if case % 3 else 1e3)   # a scene far from the origin
+        world = []
+        for i in range(n):
+            c = offset + rng.normal(size=3) * spread * (0.01 if rng.random() < 0.2 else 1.0)
+            if world and rng.random() < 0.1:
+                c = np.array(world[-1]["hittable/center"])                  # coincident centres
+            r = scale * 10.0 ** rng.uniform(-3, 1) * (-1 if rng.random() < 0.05 else 1)
+            kind = rng.integers(0, 3)
+            m = (mat.lambertian(tuple(rng.random(3))) if kind == 0 else
+                 mat.metal(tuple(rng.random(3)), float(rng.random() * 1.2)) if kind == 1 else
+                 mat.dielectric(float(rng.uniform(0.5, 2.5))))
+            world.append(S.body(sp(tuple(float(x) for x in c), float(r)), m))
+        pick = np.array(world[int(rng.integers(0, n))]["hittable/center"])
+        where = rng.integers(0, 3)
+        look_from = (pick + rng.normal(size=3) * scale * 1e-4 if where == 0 else        # inside / on a sphere
+                     pick + rng.normal(size=3) * spread * 3 if where == 1 else           # among the spheres
+                     offset + rng.normal(size=3) * spread * 10.0 ** rng.uniform(1, 4))   # far away
+        cam = CAM.main_camera(48, 27, vfov=float(rng.uniform(1, 120)), look_from=tuple(float(x) for x in look_from),
+                              look_at=tuple(float(x) for x in pick), defocus_angle=float(rng.choice([0.0, 2.0])),
+                              focus_dist=float(np.linalg.norm(look_from - pick) + 1e-9 * scale))
+        for extra in (0, _abi.F_SMEM_TABLE):
+            a, ra, sa = gpu(world, cam, 4, 12, seed=case, flags=O.FLAGS_MAIN | extra, samples_per_unit=4)
+            b, rb, sb = gpu(world, cam, 4, 12, seed=case, flags=O.FLAGS_MAIN | extra | _abi.F_NO_CULL, samples_per_unit=4)
+            assert sa["segments"] == sb["segments"] and np.array_equal(a, b, equal_nan=True), (case, extra, n, scale)
+
+
 def test_both_kernels_agree_with_the_oracle():
     """Scenes of <= 512 spheres normally run the constant-table kernel; RTCLJ_F_SMEM_TABLE sends
     them through the shared-memory-table kernel (TMA staging, survivor lists, flushes) as well."""
