@@ -135,6 +135,9 @@ def test_cull_fuzz_against_exhaustive_scan():
             a, ra, sa = gpu(world, cam, 4, 12, seed=case, flags=O.FLAGS_MAIN | extra, samples_per_unit=4)
             b, rb, sb = gpu(world, cam, 4, 12, seed=case, flags=O.FLAGS_MAIN | extra | _abi.F_NO_CULL, samples_per_unit=4)
             assert sa["segments"] == sb["segments"] and np.array_equal(a, b, equal_nan=True), (case, extra, n, scale)
+        if case % 4 == 0:   # and the whole pipeline against the CPU oracle
+            lo, ro, so = O.render(S.to_soa(world), cam, 4, 12, seed=case, flags=O.FLAGS_MAIN, threads=8, samples_per_unit=4)
+            assert so.segments == sa["segments"] and np.array_equal(lo, a, equal_nan=True) and np.array_equal(ro, ra), (case, n, scale)
 
 
 def test_both_kernels_agree_with_the_oracle():
