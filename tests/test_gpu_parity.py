@@ -131,12 +131,13 @@ def test_cull_fuzz_against_exhaustive_scan():
         cam = CAM.main_camera(48, 27, vfov=float(rng.uniform(1, 120)), look_from=tuple(float(x) for x in look_from),
                               look_at=tuple(float(x) for x in pick), defocus_angle=float(rng.choice([0.0, 2.0])),
                               focus_dist=float(np.linalg.norm(look_from - pick) + 1e-9 * scale))
+        variant = O.FLAGS_REALM if case % 2 else O.FLAGS_MAIN   # forward / innermost-first product, Schlick on / off
         for extra in (0, _abi.F_SMEM_TABLE):
-            a, ra, sa = gpu(world, cam, 4, 12, seed=case, flags=O.FLAGS_MAIN | extra, samples_per_unit=4)
-            b, rb, sb = gpu(world, cam, 4, 12, seed=case, flags=O.FLAGS_MAIN | extra | _abi.F_NO_CULL, samples_per_unit=4)
+            a, ra, sa = gpu(world, cam, 4, 12, seed=case, flags=variant | extra, samples_per_unit=4)
+            b, rb, sb = gpu(world, cam, 4, 12, seed=case, flags=variant | extra | _abi.F_NO_CULL, samples_per_unit=4)
             assert sa["segments"] == sb["segments"] and np.array_equal(a, b, equal_nan=True), (case, extra, n, scale)
         if case % 4 == 0:   # and the whole pipeline against the CPU oracle
-            lo, ro, so = O.render(S.to_soa(world), cam, 4, 12, seed=case, flags=O.FLAGS_MAIN, threads=8, samples_per_unit=4)
+            lo, ro, so = O.render(S.to_soa(world), cam, 4, 12, seed=case, flags=variant, threads=8, samples_per_unit=4)
             assert so.segments == sa["segments"] and np.array_equal(lo, a, equal_nan=True) and np.array_equal(ro, ra), (case, n, scale)
 
 
