@@ -76,7 +76,9 @@ enum {
   RTCLJ_F_NORMAL_SHADING = 16u, /* hit -> 0.5*(N+1), no bounces, raytracing_i.clj:59-73     */
   RTCLJ_F_QUANT_LINEAR = 32u,   /* 8-bit = int(255.999*c), no gamma, raytracing_i.clj:170   */
   RTCLJ_F_NO_CULL = 1u << 16,   /* debugging: skip the fp32 cull, test every sphere in fp64 */
-  RTCLJ_F_SMEM_TABLE = 1u << 17 /* testing: use the shared-memory-table kernel even for a small scene */
+  RTCLJ_F_SMEM_TABLE = 1u << 17, /* testing: use the shared-memory-table kernel even for a small scene */
+  RTCLJ_F_LANE_KERNEL = 1u << 18 /* testing: scenes of <= 512 spheres on the round-1 kernel (one path per
+                                    lane) instead of the wavefront kernel; same image, for A/B timing */
 };
 #define RTCLJ_FLAGS_MAIN                                                               \
   (RTCLJ_F_NEAR_ZERO_GUARD | RTCLJ_F_SCHLICK | RTCLJ_F_REVERSE_PRODUCT | RTCLJ_F_MEAN_DIVIDE)
@@ -120,10 +122,13 @@ typedef struct rtclj_params {
   int32_t max_depth; /* max-depth      */
   uint64_t seed;     /* Philox key; the stream is keyed by (pixel, sample, bounce) */
   uint32_t flags;    /* RTCLJ_F_*      */
-  /* Samples summed sequentially per work unit.  <=0: the library chooses (reported in
-   * rtclj_stats.samples_per_unit); >= spp: one sequential sum per pixel, exactly the
-   * reference's order (raytracing.clj:142-155).  Smaller units only change the
-   * association of the final additions (unit sums are added in order). */
+  /* Samples summed sequentially per work unit.  >= spp: one sequential sum per pixel, exactly the
+   * reference's order (raytracing.clj:142-155, raytracing_i.clj:146-163).  Smaller units split a
+   * pixel into chunks whose sums are added in index order: only the association of <= spp
+   * additions changes (<= 1e-13 relative), and load balance improves.  <= 0: the library chooses,
+   * from the image size alone (reported in rtclj_stats.samples_per_unit): the strict sequential sum
+   * when max_depth == 1 or RTCLJ_F_NORMAL_SHADING is set (primary-ray renders, whose contract is
+   * bit-exactness), chunks otherwise. */
   int32_t samples_per_unit;
   /* Row sharding for one-process-per-GPU hosts: rows are cut into tiles of
    * `shard_rows` rows and tile t belongs to shard t % shard_count.  A sharded render
@@ -163,11 +168,24 @@ int rtclj_render(const rtclj_scene *scene, const rtclj_camera *camera,
                  const rtclj_params *params, double *out_linear, uint8_t *out_rgb8,
                  rtclj_stats *stats);
 
-/* The same image, rows interleaved over `n_devices` GPUs driven by this one process;
- * params->shard_* and params->device are ignored. */
+/* The same image, rows interleaved over `n_devices` GPUs driven by this ONE process -- the call a JVM
+ * host makes where the reference starts its pool (src/raytracing.clj:157-171).  One worker thread per
+ * device uploads, renders and downloads its shard, so the devices overlap; rows are cut into tiles of
+ * params->shard_rows rows (<= 0: 1) and tile t goes to devices[t % n_devices].  params->shard_index,
+ * shard_count and device are ignored.  The image is identical for any device list. */
 int rtclj_render_multi(const rtclj_scene *scene, const rtclj_camera *camera,
                        const rtclj_params *params, const int32_t *devices, int32_t n_devices,
                        double *out_linear, uint8_t *out_rgb8, rtclj_stats *stats);
+
+/* Pinned host memory.  Output images that live in memory CUDA knows as pinned are written by the GPUs
+ * directly and asynchronously; pageable images (malloc, numpy, a JVM Arena) are filled through pinned
+ * staging buffers inside the library (one extra host copy).  rtclj_host_alloc returns pinned memory
+ * (Panama: MemorySegment.ofAddress(p).reinterpret(bytes)); rtclj_host_register pins memory the caller
+ * already owns (page-aligned ranges register fastest) until rtclj_host_unregister. */
+int rtclj_host_alloc(size_t bytes, void **out);
+int rtclj_host_free(void *p);
+int rtclj_host_register(void *p, size_t bytes);
+int rtclj_host_unregister(void *p);
 
 /* Device-resident path. */
 int rtclj_ctx_create(int32_t device, rtclj_ctx **out);
@@ -175,7 +193,10 @@ void rtclj_ctx_destroy(rtclj_ctx *ctx);
 int rtclj_ctx_set_scene(rtclj_ctx *ctx, const rtclj_scene *scene);
 /* Enqueues the render on `stream` (a cudaStream_t, NULL = the default stream) and
  * returns without synchronising.  d_out_linear / d_out_rgb8 are DEVICE pointers to
- * full-size images (either may be NULL). */
+ * full-size images (either may be NULL).  One context serves one stream at a time: its
+ * work buffers belong to the render in flight (rtclj_ctx_set_scene waits for it).  Different
+ * contexts -- also on one device, with different scenes -- may render concurrently: a launch
+ * carries its cull table with it (kernel parameters), the library holds no per-device state. */
 int rtclj_ctx_render(rtclj_ctx *ctx, const rtclj_camera *camera, const rtclj_params *params,
                      void *d_out_linear, void *d_out_rgb8, void *stream);
 /* Synchronises `stream` and reads the counters of the last rtclj_ctx_render. */

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("RTCLJ_LIB") or os.path.join(HERE, "librtclj_b200.so")
 
 LAMBERTIAN, METAL, DIELECTRIC = 0, 1, 2
 F_NEAR_ZERO_GUARD, F_SCHLICK, F_REVERSE_PRODUCT, F_MEAN_DIVIDE = 1, 2, 4, 8
-F_NORMAL_SHADING, F_QUANT_LINEAR, F_NO_CULL, F_SMEM_TABLE = 16, 32, 1 << 16, 1 << 17
+F_NORMAL_SHADING, F_QUANT_LINEAR, F_NO_CULL, F_SMEM_TABLE, F_LANE_KERNEL = 16, 32, 1 << 16, 1 << 17, 1 << 18
 FLAGS_MAIN = F_NEAR_ZERO_GUARD | F_SCHLICK | F_REVERSE_PRODUCT | F_MEAN_DIVIDE
 FLAGS_REALM = 0
 FLAGS_I = F_NORMAL_SHADING | F_QUANT_LINEAR
@@ -56,6 +56,10 @@ SYMBOLS = {
     "rtclj_render_multi": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Params),
                                      C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p,
                                      C.POINTER(Stats)]),
+    "rtclj_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rtclj_host_free": (C.c_int, [C.c_void_p]),
+    "rtclj_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "rtclj_host_unregister": (C.c_int, [C.c_void_p]),
     "rtclj_ctx_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "rtclj_ctx_destroy": (None, [C.c_void_p]),
     "rtclj_ctx_set_scene": (C.c_int, [C.c_void_p, C.POINTER(Scene)]),

@@ -3,7 +3,9 @@
 // table), work-unit sizing, launches, copies.  No CPU fallback anywhere in this file.
 #include "../../include/rtclj_b200.h"
 #include "rtclj_kernels.cuh"
+#include "rtclj_wave_kernel.cuh"
 #include "rtclj_p3_kernels.cuh"
+#include "rtclj_error.h"
 
 #include <algorithm>
 #include <chrono>
@@ -11,25 +13,18 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace rtclj;
 
 namespace {
 
-thread_local std::string g_err;
-
-int fail(int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  g_err = buf;
-  return code;
-}
+#define fail rtclj_fail  // the thread-local message lives in rtclj_host.cpp (rtclj_error.h)
 
 #define CU(call)                                                                          \
   do {                                                                                    \
@@ -75,16 +70,25 @@ struct rtclj_ctx {
   DevBuf<double> partial;
   DevBuf<unsigned long long> counters;  // [0] queue, [1..4] stats
   DevBuf<unsigned short> stack;
+  DevBuf<unsigned> arrive;              // wavefront kernel: chunk arrival counters per pixel
+  std::vector<float> ctab_host;         // the cull table of a small scene: launched as a kernel parameter
+  KParams kparams;                      // launch parameters of the last render (8.4 KB with the table)
   DevBuf<double> out_linear;            // used by the host-buffer entry points
   DevBuf<unsigned char> out_rgb8;
   DevBuf<unsigned long long> p3_state;  // P3 writer: ticket, total, text bytes per CTA run
   int p3_ctas_per_sm = 0;
   DevBuf<unsigned char> p3_in, p3_text; // staging for the host-buffer entry point
   float p3_count_ms = 0.f, p3_write_ms = 0.f;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;  // render: start, kernel end, finalize end
+  cudaEvent_t p3_ev0 = nullptr, p3_ev1 = nullptr;           // the P3 writer's own timing events
   cudaStream_t own_stream = nullptr;
   int last_spu = 0;
   bool have_scene = false;
+  bool render_pending = false;  // a render has been enqueued since the last scene upload / stats
+  // pinned staging for downloads into PAGEABLE caller memory (two buffers, pipelined)
+  void* pin[2] = {nullptr, nullptr};
+  size_t pin_cap = 0;
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -189,7 +193,6 @@ __global__ void __launch_bounds__(512) peak_kernel(float* out, int iters, float 
 extern "C" {
 
 int rtclj_abi_version(void) { return RTCLJ_ABI_VERSION; }
-const char* rtclj_last_error(void) { return g_err.c_str(); }
 
 int rtclj_device_count(int* count) {
   if (!count) return fail(RTCLJ_E_INVALID, "null count");
@@ -199,6 +202,8 @@ int rtclj_device_count(int* count) {
   *count = n;
   return RTCLJ_OK;
 }
+
+void rtclj_ctx_destroy(rtclj_ctx* c);
 
 int rtclj_ctx_create(int32_t device, rtclj_ctx** out) {
   if (!out) return fail(RTCLJ_E_INVALID, "null out");
@@ -213,30 +218,39 @@ int rtclj_ctx_create(int32_t device, rtclj_ctx** out) {
   CU(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10)
     return fail(RTCLJ_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-  rtclj_ctx* c = new rtclj_ctx();
+  // owned until every CUDA call below has succeeded: a failure frees what was created
+  std::unique_ptr<rtclj_ctx, void (*)(rtclj_ctx*)> guard(new (std::nothrow) rtclj_ctx(), rtclj_ctx_destroy);
+  rtclj_ctx* c = guard.get();
+  if (!c) return fail(RTCLJ_E_CUDA, "out of host memory");
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreate(&c->ev2));
+  CU(cudaEventCreate(&c->p3_ev0));
+  CU(cudaEventCreate(&c->p3_ev1));
+  CU(cudaEventCreateWithFlags(&c->pin_ev[0], cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->pin_ev[1], cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CU(c->counters.reserve(8));
   CU(cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   CU(cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-  *out = c;
+  CU(cudaFuncSetAttribute(render_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WaveSmem::total));
+  *out = guard.release();
   return RTCLJ_OK;
 }
 
 void rtclj_ctx_destroy(rtclj_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   c->geom32.release(); c->geom64.release(); c->mat.release(); c->partial.release();
-  c->counters.release(); c->stack.release(); c->out_linear.release(); c->out_rgb8.release();
+  c->counters.release(); c->stack.release(); c->arrive.release(); c->out_linear.release(); c->out_rgb8.release();
   c->p3_state.release(); c->p3_in.release(); c->p3_text.release();
-  if (c->ev0) cudaEventDestroy(c->ev0);
-  if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->ev2) cudaEventDestroy(c->ev2);
+  for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->p3_ev0, c->p3_ev1, c->pin_ev[0], c->pin_ev[1]})
+    if (e) cudaEventDestroy(e);
+  for (void* h : c->pin) if (h) cudaFreeHost(h);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -265,6 +279,9 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
     if (!(reach < 1e18)) return fail(RTCLJ_E_INVALID, "sphere %d: coordinates beyond 1e18 are not supported", i);
   }
   CU(cudaSetDevice(c->device));
+  // rtclj_ctx_render is asynchronous and may run on a non-blocking stream, which the blocking copies
+  // below do not wait for: let the last render finish before its tables change
+  if (c->render_pending) { CU(cudaEventSynchronize(c->ev2)); c->render_pending = false; }
 
   // translation for the fp32 cull: per-axis median of the centres keeps |C - shift|
   // (and with it the inflation of the conservative test) small where the spheres are
@@ -328,6 +345,8 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
     CU(cudaMemcpy(c->geom32.p, g32.data(), sizeof(float) * 4 * (size_t)npad, cudaMemcpyHostToDevice));
   }
   c->n = n; c->nhalf = nhalf;
+  c->ctab_host.clear();
+  if (use_const_table(nhalf)) c->ctab_host.assign(g32.begin(), g32.begin() + (size_t)npad * 4);
   std::memcpy(c->shift, shift, sizeof shift);
   c->have_scene = true;
   return RTCLJ_OK;
@@ -347,7 +366,12 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   const int shard_index = shard_count > 1 ? prm->shard_index : 0;
   const int shard_rows = shard_count > 1 ? prm->shard_rows : H;
   const int local_rows = local_rows_of(H, shard_index, shard_count, shard_rows);
-  int spu = prm->samples_per_unit > 0 ? prm->samples_per_unit : auto_samples_per_unit(W, H, prm->spp);
+  // Summation unit.  Primary-ray renders (max-depth 1, normal shading) are bit-exact contracts and short
+  // paths: they default to the reference's strict sequential sum (raytracing.clj:142-155,
+  // raytracing_i.clj:146-163); other renders split a pixel into chunks for load balance.
+  const bool primary_only = prm->max_depth == 1 || (prm->flags & RTCLJ_F_NORMAL_SHADING);
+  int spu = prm->samples_per_unit > 0 ? prm->samples_per_unit
+                                      : (primary_only ? prm->spp : auto_samples_per_unit(W, H, prm->spp));
   if (spu > prm->spp) spu = prm->spp;
   const int nchunks = (prm->spp + spu - 1) / spu;
   const unsigned long long local_pixels = (unsigned long long)local_rows * (unsigned long long)W;
@@ -358,16 +382,20 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
 
   CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), stream));
   if (total_units == 0) return RTCLJ_OK;
-  CU(c->partial.reserve((size_t)total_units * 3));
 
   const int grid = c->sm_count;
   const bool run_kernel = prm->max_depth > 0;
+  const bool const_tab = use_const_table(c->nhalf) && !(prm->flags & RTCLJ_F_SMEM_TABLE);
+  // scenes of <= 512 spheres: the wavefront kernel, which also finishes the pixels itself
+  const bool wave = run_kernel && const_tab && !(prm->flags & RTCLJ_F_LANE_KERNEL);
+  const bool want_out = d_out_linear || d_out_rgb8;
+  if (!wave || nchunks > 1) CU(c->partial.reserve((size_t)total_units * 3));
   CU(cudaEventRecord(c->ev0, stream));
   if (!run_kernel) {
     CU(cudaMemsetAsync(c->partial.p, 0, (size_t)total_units * 3 * sizeof(double), stream));  // depth <= 0: black
   } else {
-    KParams P;
-    std::memset(&P, 0, sizeof P);
+    KParams& P = c->kparams;  // 8.4 KB with the table: kept in the context, not on the stack of a JVM thread
+    std::memset(&P, 0, offsetof(KParams, ctab));
     for (int a = 0; a < 3; ++a) {
       P.p00[a] = cam->pixel00[a]; P.du[a] = cam->pixel_du[a]; P.dv[a] = cam->pixel_dv[a];
       P.center[a] = cam->center[a]; P.ddu[a] = cam->defocus_u[a]; P.ddv[a] = cam->defocus_v[a];
@@ -376,7 +404,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.use_defocus = !(cam->defocus_angle <= 0.0);
     P.W = W; P.H = H; P.spp = prm->spp; P.max_depth = prm->max_depth;
     P.flags = prm->flags; P.k0 = (unsigned)prm->seed; P.k1 = (unsigned)(prm->seed >> 32);
-    P.n = c->n; P.nblocks = c->nhalf / 2; P.tail8 = c->nhalf & 1; P.geom_bytes = (unsigned)c->nhalf * 256u;
+    P.n = c->n; P.nblocks = c->nhalf / 2; P.tail8 = c->nhalf & 1;
     P.nconst = (c->n + 2 * kCBP - 1) / (2 * kCBP);
     P.smem_blocks = smem_table_blocks(c->smem_optin);
     P.geom_bytes = (unsigned)std::min((size_t)c->nhalf * 256, (size_t)P.smem_blocks * 512);  // staged part
@@ -384,33 +412,47 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
     P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
     P.partial = c->partial.p; P.queue = c->counters.p; P.stats = c->counters.p + 1;
-    const bool const_tab = use_const_table(c->nhalf) && !(prm->flags & RTCLJ_F_SMEM_TABLE);
-    P.stack_stride = (unsigned)grid * (unsigned)threads_of(const_tab);
-    if (prm->flags & RTCLJ_F_REVERSE_PRODUCT) {
-      CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
-      P.stack = c->stack.p;
-    }
-    if (const_tab) {
-      // small scene: the cull table goes to constant memory (uniform operands), stream-ordered
-      if (c->nhalf) CU(cudaMemcpyToSymbolAsync(g_ctab, c->geom32.p, (size_t)((c->n + 31) / 32) * 512, 0, cudaMemcpyDeviceToDevice, stream));
-      render_kernel<true><<<grid, threads_of(true), smem_needed(c->nhalf, true, c->smem_optin), stream>>>(P);
+    if (const_tab && !c->ctab_host.empty())
+      std::memcpy(P.ctab, c->ctab_host.data(), std::min(sizeof P.ctab, c->ctab_host.size() * sizeof(float)));
+    if (wave) {
+      P.stack_stride = (unsigned)grid * (unsigned)kWS;
+      if (prm->max_depth > 1) {  // the attenuating hits of a path, for either product order
+        CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
+        P.stack = c->stack.p;
+      }
+      P.out_linear = (double*)d_out_linear; P.out_rgb8 = (unsigned char*)d_out_rgb8;
+      if (nchunks > 1 && want_out) {
+        CU(c->arrive.reserve((size_t)local_pixels));
+        CU(cudaMemsetAsync(c->arrive.p, 0, (size_t)local_pixels * sizeof(unsigned), stream));
+        P.arrive = c->arrive.p;
+      }
+      render_wave_kernel<<<grid, kWT, WaveSmem::total, stream>>>(P);
     } else {
-      render_kernel<false><<<grid, threads_of(false), smem_needed(c->nhalf, false, c->smem_optin), stream>>>(P);
+      P.stack_stride = (unsigned)grid * (unsigned)threads_of(const_tab);
+      if (prm->flags & RTCLJ_F_REVERSE_PRODUCT) {
+        CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
+        P.stack = c->stack.p;
+      }
+      if (const_tab)
+        render_kernel<true><<<grid, threads_of(true), smem_needed(c->nhalf, true, c->smem_optin), stream>>>(P);
+      else
+        render_kernel<false><<<grid, threads_of(false), smem_needed(c->nhalf, false, c->smem_optin), stream>>>(P);
     }
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(c->ev1, stream));
-  FParams F;
-  F.partial = c->partial.p; F.out_linear = (double*)d_out_linear; F.out_rgb8 = (unsigned char*)d_out_rgb8;
-  F.W = W; F.spp = prm->spp; F.nchunks = nchunks;
-  F.shard_index = shard_index; F.shard_count = shard_count; F.shard_rows = shard_rows;
-  F.flags = prm->flags; F.local_pixels = local_pixels;
-  if (d_out_linear || d_out_rgb8) {
+  if (!wave && want_out) {
+    FParams F;
+    F.partial = c->partial.p; F.out_linear = (double*)d_out_linear; F.out_rgb8 = (unsigned char*)d_out_rgb8;
+    F.W = W; F.spp = prm->spp; F.nchunks = nchunks;
+    F.shard_index = shard_index; F.shard_count = shard_count; F.shard_rows = shard_rows;
+    F.flags = prm->flags; F.local_pixels = local_pixels;
     const unsigned blocks = (unsigned)((local_pixels + 255) / 256);
     finalize_kernel<<<blocks, 256, 0, stream>>>(F);
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(c->ev2, stream));
+  c->render_pending = true;
   return RTCLJ_OK;
 }
 
@@ -428,149 +470,265 @@ int rtclj_ctx_stats(rtclj_ctx* c, void* stream_, rtclj_stats* st) {
   if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) st->kernel_ms = ms; else cudaGetLastError();
   st->samples_per_unit = c->last_spu;
   st->n_devices = 1;
+  c->render_pending = false;
   return RTCLJ_OK;
 }
 
-// Copies the rows a shard owns from the device images to the host images.  The shard's tiles lie at a
-// regular pitch (shard_count tiles apart), so all full tiles go in ONE strided 2-D copy per image;
-// a ragged last tile follows on its own.
-static int download_rows(rtclj_ctx* c, const rtclj_camera* cam, int shard_index, int shard_count,
-                         int shard_rows, double* out_linear, uint8_t* out_rgb8, cudaStream_t stream) {
-  const size_t W = (size_t)cam->width, H = (size_t)cam->height;
-  if (shard_count <= 1) { shard_index = 0; shard_rows = (int)H; shard_count = 1; }
-  const size_t sr = (size_t)shard_rows;
-  const size_t ntiles = (H + sr - 1) / sr;
-  if ((size_t)shard_index >= ntiles) return RTCLJ_OK;
-  size_t mine = (ntiles - (size_t)shard_index + (size_t)shard_count - 1) / (size_t)shard_count;  // tiles of this shard
-  const size_t last = (size_t)shard_index + (mine - 1) * (size_t)shard_count;                     // its last tile
-  const size_t last_rows = std::min(sr, H - last * sr);
-  const size_t full = last_rows == sr ? mine : mine - 1;  // tiles of exactly shard_rows rows
-  auto copy = [&](void* dst, const void* src, size_t elem) -> cudaError_t {
-    const size_t row_bytes = W * 3 * elem;
-    const size_t first = (size_t)shard_index * sr * row_bytes;
-    cudaError_t e = cudaSuccess;
-    if (full) {
-      const size_t pitch = (size_t)shard_count * sr * row_bytes;
-      e = cudaMemcpy2DAsync((char*)dst + first, pitch, (const char*)src + first, pitch, sr * row_bytes, full,
-                            cudaMemcpyDeviceToHost, stream);
-    }
-    if (e == cudaSuccess && full != mine) {
-      const size_t off = last * sr * row_bytes;
-      e = cudaMemcpyAsync((char*)dst + off, (const char*)src + off, last_rows * row_bytes, cudaMemcpyDeviceToHost, stream);
-    }
-    return e;
-  };
-  if (out_linear) CU(copy(out_linear, c->out_linear.p, sizeof(double)));
-  if (out_rgb8) CU(copy(out_rgb8, c->out_rgb8.p, 1));
-  return RTCLJ_OK;
-}
+// ---------------------------------------------------------------- downloads into caller memory
+// A shard owns tiles of `shard_rows` rows at a regular pitch (shard_count tiles apart); the device image
+// has the full-size layout, so device and host offsets are the same.  Caller memory that CUDA knows as
+// pinned (rtclj_host_alloc / rtclj_host_register / cudaHostAlloc) is written directly by asynchronous
+// copies.  Pageable memory (numpy, malloc, a JVM Arena) goes through two pinned staging buffers of the
+// context, pipelined: the device fills one while the host unpacks the other -- a device-to-pageable
+// cudaMemcpyAsync would block the calling thread until the render in front of it has finished.
+}  // extern "C"
 
 namespace {
-std::mutex g_ctx_mu;
-std::mutex g_host_call_mu;  // the cached contexts are shared: one host-buffer call at a time
-std::vector<rtclj_ctx*> g_ctx_cache;  // one cached context per device for the host-buffer calls
 
-int cached_ctx(int device, rtclj_ctx** out) {
-  std::lock_guard<std::mutex> lk(g_ctx_mu);
-  if ((int)g_ctx_cache.size() <= device) g_ctx_cache.resize((size_t)device + 1, nullptr);
-  if (!g_ctx_cache[(size_t)device]) {
-    int rc = rtclj_ctx_create(device, &g_ctx_cache[(size_t)device]);
-    if (rc) return rc;
+struct Piece { size_t off, pitch, width, height; };  // `height` runs of `width` bytes, `pitch` apart, from `off`
+
+void plan_pieces(size_t H, size_t row_bytes, int shard_index, int shard_count, int shard_rows, size_t cap,
+                 std::vector<Piece>& out) {
+  if (shard_count <= 1) { shard_index = 0; shard_count = 1; shard_rows = (int)H; }
+  const size_t sr = (size_t)shard_rows;
+  const size_t ntiles = (H + sr - 1) / sr;
+  if ((size_t)shard_index >= ntiles) return;
+  const size_t mine = (ntiles - (size_t)shard_index + (size_t)shard_count - 1) / (size_t)shard_count;
+  const size_t last = (size_t)shard_index + (mine - 1) * (size_t)shard_count;  // this shard's last tile
+  const size_t last_rows = std::min(sr, H - last * sr);
+  const size_t full = last_rows == sr ? mine : mine - 1;  // tiles of exactly shard_rows rows
+  const size_t tile_bytes = sr * row_bytes, pitch = (size_t)shard_count * tile_bytes;
+  const size_t first = (size_t)shard_index * tile_bytes;
+  auto split = [&](size_t off, size_t bytes) {  // one contiguous run, in pieces of at most `cap` bytes
+    for (size_t o = 0; o < bytes; o += cap) out.push_back(Piece{off + o, 0, std::min(cap, bytes - o), 1});
+  };
+  if (tile_bytes >= cap) {
+    for (size_t t = 0; t < full; ++t) split(first + t * pitch, tile_bytes);
+  } else {
+    const size_t group = cap / tile_bytes;  // whole tiles per piece: one strided 2-D copy
+    for (size_t t = 0; t < full; t += group) out.push_back(Piece{first + t * pitch, pitch, tile_bytes, std::min(group, full - t)});
   }
-  *out = g_ctx_cache[(size_t)device];
+  if (full != mine) split(last * tile_bytes, last_rows * row_bytes);
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+constexpr size_t kStageBytes = 16u << 20;
+
+int download_image(rtclj_ctx* c, const std::vector<Piece>& pieces, char* host, const char* dev, cudaStream_t stream) {
+  if (pieces.empty()) return RTCLJ_OK;
+  if (is_pinned(host)) {  // asynchronous all the way: the caller's stats call synchronises
+    for (const Piece& p : pieces) {
+      if (p.height == 1) CU(cudaMemcpyAsync(host + p.off, dev + p.off, p.width, cudaMemcpyDeviceToHost, stream));
+      else CU(cudaMemcpy2DAsync(host + p.off, p.pitch, dev + p.off, p.pitch, p.width, p.height, cudaMemcpyDeviceToHost, stream));
+    }
+    return RTCLJ_OK;
+  }
+  if (!c->pin[0]) {
+    CU(cudaHostAlloc(&c->pin[0], kStageBytes, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->pin[1], kStageBytes, cudaHostAllocDefault));
+    c->pin_cap = kStageBytes;
+  }
+  auto unpack = [&](size_t i) {
+    const Piece& p = pieces[i];
+    const char* src = (const char*)c->pin[i & 1];
+    for (size_t r = 0; r < p.height; ++r) std::memcpy(host + p.off + r * p.pitch, src + r * p.width, p.width);
+  };
+  for (size_t i = 0; i < pieces.size(); ++i) {
+    const int b = (int)(i & 1);
+    if (i >= 2) { CU(cudaEventSynchronize(c->pin_ev[b])); unpack(i - 2); }  // this buffer's previous piece
+    const Piece& p = pieces[i];
+    if (p.height == 1) CU(cudaMemcpyAsync(c->pin[b], dev + p.off, p.width, cudaMemcpyDeviceToHost, stream));
+    else CU(cudaMemcpy2DAsync(c->pin[b], p.width, dev + p.off, p.pitch, p.width, p.height, cudaMemcpyDeviceToHost, stream));
+    CU(cudaEventRecord(c->pin_ev[b], stream));
+  }
+  for (size_t i = pieces.size() >= 2 ? pieces.size() - 2 : 0; i < pieces.size(); ++i) {
+    CU(cudaEventSynchronize(c->pin_ev[i & 1]));
+    unpack(i);
+  }
   return RTCLJ_OK;
 }
+
+int download_rows(rtclj_ctx* c, const rtclj_camera* cam, int shard_index, int shard_count, int shard_rows,
+                  double* out_linear, uint8_t* out_rgb8, cudaStream_t stream) {
+  const size_t W = (size_t)cam->width, H = (size_t)cam->height;
+  std::vector<Piece> pieces;
+  if (out_linear) {
+    plan_pieces(H, W * 3 * sizeof(double), shard_index, shard_count, shard_rows, kStageBytes, pieces);
+    int rc = download_image(c, pieces, (char*)out_linear, (const char*)c->out_linear.p, stream);
+    if (rc) return rc;
+  }
+  if (out_rgb8) {
+    pieces.clear();
+    plan_pieces(H, W * 3, shard_index, shard_count, shard_rows, kStageBytes, pieces);
+    int rc = download_image(c, pieces, (char*)out_rgb8, (const char*)c->out_rgb8.p, stream);
+    if (rc) return rc;
+  }
+  return RTCLJ_OK;
+}
+
+// One cached context per device for the host-buffer entry points, each behind its OWN lock: calls on
+// different devices overlap (rtclj_render_multi, or a host that gives each pool thread a GPU), calls on
+// one device queue up.
+std::mutex g_ctx_mu;
+struct DeviceSlot { std::mutex mu; rtclj_ctx* ctx = nullptr; };
+std::vector<std::unique_ptr<DeviceSlot>> g_slots;
+
+int device_slot(int device, DeviceSlot** out) {
+  int ndev = 0;
+  int rc = rtclj_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev == 0) return fail(RTCLJ_E_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(RTCLJ_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if ((int)g_slots.size() < ndev) g_slots.resize((size_t)ndev);
+  if (!g_slots[(size_t)device]) g_slots[(size_t)device].reset(new DeviceSlot());
+  *out = g_slots[(size_t)device].get();
+  return RTCLJ_OK;
+}
+
+// scene upload + render of one shard + download into the caller's images, on one device
+int render_shard_hostbuf(const rtclj_scene* scene, const rtclj_camera* cam, const rtclj_params* prm, double* out_linear,
+                         uint8_t* out_rgb8, rtclj_stats* stats) {
+  const auto t0 = std::chrono::steady_clock::now();
+  DeviceSlot* slot = nullptr;
+  int rc = device_slot(prm->device, &slot);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(slot->mu);
+  if (!slot->ctx) { rc = rtclj_ctx_create(prm->device, &slot->ctx); if (rc) return rc; }
+  rtclj_ctx* c = slot->ctx;
+  rc = rtclj_ctx_set_scene(c, scene);
+  if (rc) return rc;
+  const size_t npix = (size_t)cam->width * (size_t)cam->height;
+  if (out_linear) CU(c->out_linear.reserve(npix * 3));
+  if (out_rgb8) CU(c->out_rgb8.reserve(npix * 3));
+  rc = rtclj_ctx_render(c, cam, prm, out_linear ? c->out_linear.p : nullptr, out_rgb8 ? c->out_rgb8.p : nullptr, c->own_stream);
+  if (rc) return rc;
+  rc = download_rows(c, cam, prm->shard_index, prm->shard_count, prm->shard_rows, out_linear, out_rgb8, c->own_stream);
+  if (rc) return rc;
+  rtclj_stats s;
+  rc = rtclj_ctx_stats(c, c->own_stream, &s);  // synchronises the stream: the direct copies have landed
+  if (rc) return rc;
+  s.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = s;
+  return RTCLJ_OK;
+}
+
+// nothing may throw across the C boundary (a JVM host would die): bad_alloc etc. become error codes
+template <class F>
+int guarded(F&& f) {
+  try { return f(); }
+  catch (const std::bad_alloc&) { return fail(RTCLJ_E_CUDA, "out of host memory"); }
+  catch (const std::exception& e) { return fail(RTCLJ_E_CUDA, "unexpected exception: %s", e.what()); }
+  catch (...) { return fail(RTCLJ_E_CUDA, "unexpected exception"); }
+}
+
 }  // namespace
 
+extern "C" {
+
+// The image rows interleaved over several GPUs, driven by this ONE process -- what a JVM host calls
+// where the reference starts its pool (src/raytracing.clj:157-171).  One worker thread per device runs
+// upload -> render -> download for its shard, so the devices render AND copy at the same time; the
+// shards' rows are disjoint, the image needs no further gather.
 int rtclj_render_multi(const rtclj_scene* scene, const rtclj_camera* cam, const rtclj_params* prm,
                        const int32_t* devices, int32_t n_devices, double* out_linear, uint8_t* out_rgb8,
                        rtclj_stats* stats) {
-  const auto t0 = std::chrono::steady_clock::now();
-  if (!scene) return fail(RTCLJ_E_INVALID, "null scene");
-  int rc = validate(cam, prm);
-  if (rc) return rc;
-  if (n_devices <= 0 || !devices) return fail(RTCLJ_E_INVALID, "empty device list");
-  int ndev = 0;
-  rc = rtclj_device_count(&ndev);
-  if (rc) return rc;
-  if (ndev == 0) return fail(RTCLJ_E_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
-  std::lock_guard<std::mutex> lk(g_host_call_mu);
-
-  const size_t npix = (size_t)cam->width * (size_t)cam->height;
-  std::vector<rtclj_ctx*> ctxs((size_t)n_devices);
-  rtclj_params p = *prm;
-  const bool single = n_devices == 1;
-  if (!single) {
-    p.shard_count = n_devices;
-    p.shard_rows = prm->shard_rows > 0 ? prm->shard_rows : 4;
-  }
-  for (int d = 0; d < n_devices; ++d) {
-    rc = cached_ctx(devices[d], &ctxs[(size_t)d]);
-    if (rc) return rc;
-    rtclj_ctx* c = ctxs[(size_t)d];
-    rc = rtclj_ctx_set_scene(c, scene);
-    if (rc) return rc;
-    if (out_linear) CU(c->out_linear.reserve(npix * 3));
-    if (out_rgb8) CU(c->out_rgb8.reserve(npix * 3));
-  }
-  for (int d = 0; d < n_devices; ++d) {  // enqueue everything, then wait: devices overlap
-    rtclj_ctx* c = ctxs[(size_t)d];
-    if (!single) p.shard_index = d;
-    rc = rtclj_ctx_render(c, cam, &p, out_linear ? c->out_linear.p : nullptr,
-                          out_rgb8 ? c->out_rgb8.p : nullptr, c->own_stream);
-    if (rc) return rc;
-    rc = download_rows(c, cam, p.shard_index, p.shard_count, p.shard_rows, out_linear, out_rgb8, c->own_stream);
-    if (rc) return rc;
-  }
-  rtclj_stats total;
-  std::memset(&total, 0, sizeof total);
-  for (int d = 0; d < n_devices; ++d) {
-    rtclj_stats s;
-    rc = rtclj_ctx_stats(ctxs[(size_t)d], ctxs[(size_t)d]->own_stream, &s);
-    if (rc) return rc;
-    total.samples += s.samples; total.segments += s.segments; total.exact_tests += s.exact_tests;
-    total.list_overflows += s.list_overflows; total.prefilter_tests += s.prefilter_tests;
-    total.device_ms = std::max(total.device_ms, s.device_ms);
-    total.kernel_ms = std::max(total.kernel_ms, s.kernel_ms);
-    total.samples_per_unit = s.samples_per_unit;
-  }
-  total.n_devices = n_devices;
-  total.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (stats) *stats = total;
-  return RTCLJ_OK;
-}
-
-int rtclj_render(const rtclj_scene* scene, const rtclj_camera* cam, const rtclj_params* prm, double* out_linear,
-                 uint8_t* out_rgb8, rtclj_stats* stats) {
-  if (!prm) return fail(RTCLJ_E_INVALID, "null params");
-  if (prm->shard_count > 1) {
-    // one shard of the image on one device (one-process-per-GPU hosts)
+  return guarded([&]() -> int {
     const auto t0 = std::chrono::steady_clock::now();
     if (!scene) return fail(RTCLJ_E_INVALID, "null scene");
     int rc = validate(cam, prm);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(g_host_call_mu);
-    rtclj_ctx* c = nullptr;
-    rc = cached_ctx(prm->device, &c);
+    if (n_devices <= 0 || !devices) return fail(RTCLJ_E_INVALID, "empty device list");
+    int ndev = 0;
+    rc = rtclj_device_count(&ndev);
     if (rc) return rc;
-    rc = rtclj_ctx_set_scene(c, scene);
-    if (rc) return rc;
-    const size_t npix = (size_t)cam->width * (size_t)cam->height;
-    if (out_linear) CU(c->out_linear.reserve(npix * 3));
-    if (out_rgb8) CU(c->out_rgb8.reserve(npix * 3));
-    rc = rtclj_ctx_render(c, cam, prm, out_linear ? c->out_linear.p : nullptr, out_rgb8 ? c->out_rgb8.p : nullptr, c->own_stream);
-    if (rc) return rc;
-    rc = download_rows(c, cam, prm->shard_index, prm->shard_count, prm->shard_rows, out_linear, out_rgb8, c->own_stream);
-    if (rc) return rc;
-    rtclj_stats s;
-    rc = rtclj_ctx_stats(c, c->own_stream, &s);
-    if (rc) return rc;
-    s.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (stats) *stats = s;
+    if (ndev == 0) return fail(RTCLJ_E_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    for (int d = 0; d < n_devices; ++d) {
+      if (devices[d] < 0 || devices[d] >= ndev) return fail(RTCLJ_E_INVALID, "device %d out of range [0,%d)", devices[d], ndev);
+      for (int e = 0; e < d; ++e)
+        if (devices[e] == devices[d]) return fail(RTCLJ_E_INVALID, "device %d listed twice", devices[d]);
+    }
+    std::vector<rtclj_params> p((size_t)n_devices, *prm);
+    std::vector<rtclj_stats> st((size_t)n_devices);
+    std::vector<int> rcs((size_t)n_devices, RTCLJ_OK);
+    std::vector<std::string> msgs((size_t)n_devices);
+    for (int d = 0; d < n_devices; ++d) {
+      p[(size_t)d].device = devices[d];
+      if (n_devices > 1) {
+        p[(size_t)d].shard_index = d;
+        p[(size_t)d].shard_count = n_devices;
+        p[(size_t)d].shard_rows = prm->shard_rows > 0 ? prm->shard_rows : 1;  // 1-row tiles balance best
+      } else {
+        p[(size_t)d].shard_index = 0; p[(size_t)d].shard_count = 1; p[(size_t)d].shard_rows = 0;
+      }
+    }
+    auto work = [&](int d) {
+      rcs[(size_t)d] = guarded([&]() { return render_shard_hostbuf(scene, cam, &p[(size_t)d], out_linear, out_rgb8, &st[(size_t)d]); });
+      if (rcs[(size_t)d]) msgs[(size_t)d] = rtclj_error_get();  // the message is thread-local: carry it over
+    };
+    std::vector<std::thread> pool;
+    for (int d = 1; d < n_devices; ++d) pool.emplace_back(work, d);
+    work(0);
+    for (std::thread& t : pool) t.join();
+    rtclj_stats total;
+    std::memset(&total, 0, sizeof total);
+    for (int d = 0; d < n_devices; ++d) {
+      if (rcs[(size_t)d]) { rtclj_error_set(msgs[(size_t)d].c_str()); return rcs[(size_t)d]; }
+      const rtclj_stats& s = st[(size_t)d];
+      total.samples += s.samples; total.segments += s.segments; total.exact_tests += s.exact_tests;
+      total.list_overflows += s.list_overflows; total.prefilter_tests += s.prefilter_tests;
+      total.device_ms = std::max(total.device_ms, s.device_ms);
+      total.kernel_ms = std::max(total.kernel_ms, s.kernel_ms);
+      total.samples_per_unit = s.samples_per_unit;
+    }
+    total.n_devices = n_devices;
+    total.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = total;
     return RTCLJ_OK;
-  }
-  const int32_t dev = prm->device;
-  return rtclj_render_multi(scene, cam, prm, &dev, 1, out_linear, out_rgb8, stats);
+  });
+}
+
+int rtclj_render(const rtclj_scene* scene, const rtclj_camera* cam, const rtclj_params* prm, double* out_linear,
+                 uint8_t* out_rgb8, rtclj_stats* stats) {
+  return guarded([&]() -> int {
+    if (!scene) return fail(RTCLJ_E_INVALID, "null scene");
+    int rc = validate(cam, prm);
+    if (rc) return rc;
+    rc = render_shard_hostbuf(scene, cam, prm, out_linear, out_rgb8, stats);
+    if (rc == RTCLJ_OK && stats) stats->n_devices = 1;
+    return rc;
+  });
+}
+
+// ---- pinned host memory for callers: images allocated (or registered) here are written by the GPUs
+// directly, with no staging copy (Panama: MemorySegment.reinterpret over the returned address)
+int rtclj_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(RTCLJ_E_INVALID, "null out");
+  *out = nullptr;
+  int ndev = 0;
+  int rc = rtclj_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev == 0) return fail(RTCLJ_E_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return RTCLJ_OK;
+}
+int rtclj_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return RTCLJ_OK;
+}
+int rtclj_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return fail(RTCLJ_E_INVALID, "null buffer");
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return RTCLJ_OK;
+}
+int rtclj_host_unregister(void* p) {
+  if (p) CU(cudaHostUnregister(p));
+  return RTCLJ_OK;
 }
 
 // ---- row f-1: the P3 writer (src/raytracing.clj:172-175) on the device
@@ -601,26 +759,26 @@ int rtclj_ctx_encode_ppm_p3(rtclj_ctx* c, const uint8_t* d_rgb8, int32_t width, 
   c->p3_count_ms = c->p3_write_ms = 0.f;
   if (!one_pass) {  // the exact length first: sizing calls and tighter buffers
     CU(cudaMemsetAsync(c->p3_state.p, 0, (grid + 2) * sizeof(unsigned long long), stream));
-    CU(cudaEventRecord(c->ev0, stream));
+    CU(cudaEventRecord(c->p3_ev0, stream));
     p3_encode_kernel<<<(unsigned)grid, kP3Threads, 0, stream>>>(d_rgb8, npix, aligned4, nb, per_cta, c->p3_state.p, nullptr, hdr, 1);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(c->ev2, stream));
+    CU(cudaEventRecord(c->p3_ev1, stream));
     CU(cudaMemcpyAsync(&total, c->p3_state.p + 1, sizeof total, cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
-    CU(cudaEventElapsedTime(&c->p3_count_ms, c->ev0, c->ev2));
+    CU(cudaEventElapsedTime(&c->p3_count_ms, c->p3_ev0, c->p3_ev1));
     *len = (size_t)total;
     if (!d_out) return RTCLJ_OK;
     if ((size_t)total > capacity) return fail(RTCLJ_E_BUFFER, "P3 text needs %llu bytes, capacity is %zu", total, capacity);
   }
   CU(cudaMemsetAsync(c->p3_state.p, 0, (grid + 2) * sizeof(unsigned long long), stream));
-  CU(cudaEventRecord(c->ev0, stream));
+  CU(cudaEventRecord(c->p3_ev0, stream));
   p3_encode_kernel<<<(unsigned)grid, kP3Threads, 0, stream>>>(d_rgb8, npix, aligned4, nb, per_cta, c->p3_state.p,
                                                             reinterpret_cast<unsigned char*>(d_out), hdr, 0);
   CU(cudaGetLastError());
-  CU(cudaEventRecord(c->ev1, stream));
+  CU(cudaEventRecord(c->p3_ev1, stream));
   CU(cudaMemcpyAsync(&total, c->p3_state.p + 1, sizeof total, cudaMemcpyDeviceToHost, stream));
   CU(cudaStreamSynchronize(stream));
-  CU(cudaEventElapsedTime(&c->p3_write_ms, c->ev0, c->ev1));
+  CU(cudaEventElapsedTime(&c->p3_write_ms, c->p3_ev0, c->p3_ev1));
   *len = (size_t)total;
   return RTCLJ_OK;
 }
@@ -635,10 +793,12 @@ int rtclj_ctx_encode_ms(rtclj_ctx* c, double* count_scan_ms, double* write_ms) {
 int rtclj_encode_ppm_p3_gpu(int32_t device, const uint8_t* rgb8, int32_t width, int32_t height, char* out,
                             size_t capacity, size_t* len) {
   if (width <= 0 || height <= 0 || !len || !rgb8) return fail(RTCLJ_E_INVALID, "bad image or null len");
-  std::lock_guard<std::mutex> lk(g_host_call_mu);
-  rtclj_ctx* c = nullptr;
-  int rc = cached_ctx(device, &c);
+  DeviceSlot* slot = nullptr;
+  int rc = device_slot(device, &slot);
   if (rc) return rc;
+  std::lock_guard<std::mutex> lk(slot->mu);
+  if (!slot->ctx) { rc = rtclj_ctx_create(device, &slot->ctx); if (rc) return rc; }
+  rtclj_ctx* c = slot->ctx;
   CU(cudaSetDevice(c->device));
   const size_t npix = (size_t)width * (size_t)height;
   CU(c->p3_in.reserve(npix * 3));
@@ -667,11 +827,15 @@ int rtclj_calibrate_peaks(int32_t device, double* ffma, double* ffma2, double* d
   const int sms = prop.multiProcessorCount;
   if (sm_count) *sm_count = sms;
   const int blocks = sms * 4, threads = 512, iters = 1 << 14;
-  float* out = nullptr;
-  CU(cudaMalloc(&out, sizeof(float) * (size_t)blocks * threads));
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0));
-  CU(cudaEventCreate(&e1));
+  struct Scratch {  // released on every path out of this function
+    float* out = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Scratch() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (out) cudaFree(out); }
+  } sc;
+  CU(cudaMalloc(&sc.out, sizeof(float) * (size_t)blocks * threads));
+  CU(cudaEventCreate(&sc.e0));
+  CU(cudaEventCreate(&sc.e1));
+  float* out = sc.out;
+  cudaEvent_t e0 = sc.e0, e1 = sc.e1;
   double res[3] = {0, 0, 0};
   for (int mode = 0; mode < 3; ++mode) {
     double best = 0;
@@ -690,7 +854,6 @@ int rtclj_calibrate_peaks(int32_t device, double* ffma, double* ffma2, double* d
     }
     res[mode] = best;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
   if (ffma) *ffma = res[0];
   if (ffma2) *ffma2 = res[1];
   if (dfma) *dfma = res[2];

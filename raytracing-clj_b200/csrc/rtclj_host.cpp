@@ -3,12 +3,29 @@
 // and scene generation before it.  Plain C++17, IEEE double, compiled with
 // -ffp-contract=off so the arithmetic is what the JVM (and camera.py) computes.
 #include "../../include/rtclj_b200.h"
+#include "rtclj_error.h"
 
 #include <cmath>
+#include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+
+// ---- the thread-local error message of the whole library (rtclj_last_error)
+namespace { thread_local std::string g_err; }
+int rtclj_fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+void rtclj_error_set(const char* message) { g_err = message ? message : ""; }
+const char* rtclj_error_get() { return g_err.c_str(); }
+extern "C" const char* rtclj_last_error(void) { return g_err.c_str(); }
 
 namespace {
 
@@ -63,7 +80,7 @@ struct SplitMix64 {
 extern "C" {
 
 int rtclj_quantise_rgb8(const double* linear, size_t n_values, uint32_t flags, uint8_t* out) {
-  if ((!linear || !out) && n_values) return RTCLJ_E_INVALID;
+  if ((!linear || !out) && n_values) return rtclj_fail(RTCLJ_E_INVALID, "rtclj_quantise_rgb8: null buffer");
   const bool lin = (flags & RTCLJ_F_QUANT_LINEAR) != 0;
   for (size_t i = 0; i < n_values; ++i) out[i] = (uint8_t)quantise(linear[i], lin);
   return RTCLJ_OK;
@@ -71,7 +88,7 @@ int rtclj_quantise_rgb8(const double* linear, size_t n_values, uint32_t flags, u
 
 int rtclj_encode_ppm_p3(const uint8_t* rgb8, int32_t width, int32_t height, char* out, size_t capacity,
                         size_t* len) {
-  if (width <= 0 || height <= 0 || !len) return RTCLJ_E_INVALID;
+  if (width <= 0 || height <= 0 || !len) return rtclj_fail(RTCLJ_E_INVALID, "image size must be positive and len non-null (%d x %d)", width, height);
   char header[64];
   const int hl = std::snprintf(header, sizeof header, "P3\n%d %d\n255\n", width, height);
   const size_t npix = (size_t)width * (size_t)height;
@@ -79,7 +96,7 @@ int rtclj_encode_ppm_p3(const uint8_t* rgb8, int32_t width, int32_t height, char
     *len = (size_t)hl + npix * 12 + 4;
     return RTCLJ_OK;
   }
-  if (!rgb8) return RTCLJ_E_INVALID;
+  if (!rgb8) return rtclj_fail(RTCLJ_E_INVALID, "null image");
   // "ddd" + separator slot, and the digit count, per byte value
   static const struct Lut { char s[256][4]; unsigned char n[256]; Lut() {
       for (int v = 0; v < 256; ++v) { n[v] = (unsigned char)std::snprintf(s[v], 4, "%d", v); s[v][n[v]] = ' '; }
@@ -90,7 +107,7 @@ int rtclj_encode_ppm_p3(const uint8_t* rgb8, int32_t width, int32_t height, char
     need = (size_t)hl;
     for (size_t i = 0; i < npix * 3; ++i) need += lut.n[rgb8[i]] + 1u;
     *len = need;
-    if (need > capacity) return RTCLJ_E_BUFFER;
+    if (need > capacity) return rtclj_fail(RTCLJ_E_BUFFER, "P3 text needs %zu bytes, capacity is %zu", need, capacity);
   }
   std::memcpy(out, header, (size_t)hl);
   char* w = out + hl;
@@ -157,7 +174,7 @@ inline void be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (ui
 
 int rtclj_encode_png(const uint8_t* rgb8, int32_t width, int32_t height, uint8_t* out, size_t capacity,
                      size_t* len) {
-  if (width <= 0 || height <= 0 || !len) return RTCLJ_E_INVALID;
+  if (width <= 0 || height <= 0 || !len) return rtclj_fail(RTCLJ_E_INVALID, "image size must be positive and len non-null (%d x %d)", width, height);
   const size_t row = (size_t)width * 3 + 1;          // filter byte + pixels
   const size_t raw = row * (size_t)height;           // bytes handed to deflate
   const size_t nblocks = (raw + 65534) / 65535;      // stored blocks of <= 65535 bytes
@@ -165,9 +182,9 @@ int rtclj_encode_png(const uint8_t* rgb8, int32_t width, int32_t height, uint8_t
   const size_t need = 8 + (12 + 13) + (12 + zlen) + 12;
   *len = need;
   if (!out) return RTCLJ_OK;
-  if (!rgb8) return RTCLJ_E_INVALID;
-  if (need > capacity) return RTCLJ_E_BUFFER;
-  if (zlen > 0xffffffffull) return RTCLJ_E_INVALID;
+  if (!rgb8) return rtclj_fail(RTCLJ_E_INVALID, "null image");
+  if (need > capacity) return rtclj_fail(RTCLJ_E_BUFFER, "PNG needs %zu bytes, capacity is %zu", need, capacity);
+  if (zlen > 0xffffffffull) return rtclj_fail(RTCLJ_E_INVALID, "image too large for one PNG IDAT chunk");
   static const Crc32 crc;
   static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
   uint8_t* w = out;
@@ -218,7 +235,7 @@ int rtclj_encode_png(const uint8_t* rgb8, int32_t width, int32_t height, uint8_t
 // ---- P3 reader (the input side of ppm->png): whitespace-separated decimal tokens
 int rtclj_decode_ppm_p3(const char* text, size_t len, int32_t* width, int32_t* height, uint8_t* out_rgb8,
                         size_t capacity) {
-  if (!text || !width || !height) return RTCLJ_E_INVALID;
+  if (!text || !width || !height) return rtclj_fail(RTCLJ_E_INVALID, "rtclj_decode_ppm_p3: null argument");
   size_t pos = 0;
   auto skip_ws = [&]() { while (pos < len && (text[pos] == ' ' || text[pos] == '\n' || text[pos] == '\r' || text[pos] == '\t')) ++pos; };
   auto number = [&](long long& v) -> bool {  // one non-negative decimal token
@@ -232,19 +249,19 @@ int rtclj_decode_ppm_p3(const char* text, size_t len, int32_t* width, int32_t* h
     return pos >= len || text[pos] == ' ' || text[pos] == '\n' || text[pos] == '\r' || text[pos] == '\t';
   };
   skip_ws();
-  if (pos + 2 > len || text[pos] != 'P' || text[pos + 1] != '3') return RTCLJ_E_INVALID;
+  if (pos + 2 > len || text[pos] != 'P' || text[pos + 1] != '3') return rtclj_fail(RTCLJ_E_INVALID, "not a P3 file (bad magic)");
   pos += 2;
   long long w = 0, h = 0, maxv = 0;
-  if (!number(w) || !number(h) || !number(maxv)) return RTCLJ_E_INVALID;
-  if (w <= 0 || h <= 0 || maxv > 255) return RTCLJ_E_INVALID;
+  if (!number(w) || !number(h) || !number(maxv)) return rtclj_fail(RTCLJ_E_INVALID, "P3 header: expected width, height, maximum");
+  if (w <= 0 || h <= 0 || maxv > 255) return rtclj_fail(RTCLJ_E_INVALID, "P3 header: bad dimensions or maximum > 255");
   *width = (int32_t)w;
   *height = (int32_t)h;
   if (!out_rgb8) return RTCLJ_OK;
   const size_t n = (size_t)w * (size_t)h * 3;
-  if (capacity < n) return RTCLJ_E_BUFFER;
+  if (capacity < n) return rtclj_fail(RTCLJ_E_BUFFER, "decoded image needs %zu bytes, capacity is %zu", (size_t)n, capacity);
   for (size_t i = 0; i < n; ++i) {
     long long v = 0;
-    if (!number(v) || v > maxv) return RTCLJ_E_INVALID;
+    if (!number(v) || v > maxv) return rtclj_fail(RTCLJ_E_INVALID, "P3 body: missing value or value above the maximum");
     out_rgb8[i] = (uint8_t)v;
   }
   skip_ws();
@@ -301,7 +318,7 @@ double rtclj_ratio_to_double(int64_t num, int64_t den) {
 int rtclj_camera_main(int32_t width, int32_t height, double vfov, const double look_from[3],
                       const double look_at[3], const double vup[3], double defocus_angle, double focus_dist,
                       rtclj_camera* out) {
-  if (!out || !look_from || !look_at || !vup || width <= 0 || height <= 0) return RTCLJ_E_INVALID;
+  if (!out || !look_from || !look_at || !vup || width <= 0 || height <= 0) return rtclj_fail(RTCLJ_E_INVALID, "camera: null argument or non-positive size");
   const double theta = deg_to_rad(vfov);
   const double h = std::tan(theta / 2);
   const double viewport_height = 2.0 * h * focus_dist;
@@ -327,7 +344,7 @@ int rtclj_camera_main(int32_t width, int32_t height, double vfov, const double l
 // realm/raytracing.clj:264-280, 306-322
 int rtclj_camera_realm(int32_t width, int32_t height, double vfov, const double look_from[3],
                        const double look_at[3], const double vup[3], rtclj_camera* out) {
-  if (!out || !look_from || !look_at || !vup || width <= 0 || height <= 0) return RTCLJ_E_INVALID;
+  if (!out || !look_from || !look_at || !vup || width <= 0 || height <= 0) return rtclj_fail(RTCLJ_E_INVALID, "camera: null argument or non-positive size");
   const V temp = sub(ld(look_from), ld(look_at));
   const double focal = length(temp);
   const V w = divs(temp, focal);
@@ -354,7 +371,7 @@ int rtclj_camera_realm(int32_t width, int32_t height, double vfov, const double 
 
 // experimental/raytracing_i.clj:82-90, 127-144
 int rtclj_camera_i(int32_t width, int32_t height, rtclj_camera* out) {
-  if (!out || width <= 0 || height <= 0) return RTCLJ_E_INVALID;
+  if (!out || width <= 0 || height <= 0) return rtclj_fail(RTCLJ_E_INVALID, "camera: null out or non-positive size");
   const double focal_length = 1.0, viewport_height = 2.0;
   const double viewport_width = viewport_height * rtclj_ratio_to_double(width, height);
   const V center = mk(0, 0, 0);
@@ -377,9 +394,9 @@ int rtclj_camera_i(int32_t width, int32_t height, rtclj_camera* out) {
 int rtclj_scene_random_field(uint64_t seed, int32_t lo, int32_t hi, int32_t cap, double* center_xyz,
                              double* radius, int32_t* material, double* albedo_rgb, double* fuzz, double* ior,
                              int32_t* n_out) {
-  if (!n_out || hi < lo) return RTCLJ_E_INVALID;
+  if (!n_out || hi < lo) return rtclj_fail(RTCLJ_E_INVALID, "scene_random_field: null n_out or hi < lo");
   const bool write = cap > 0;
-  if (write && (!center_xyz || !radius || !material || !albedo_rgb || !fuzz || !ior)) return RTCLJ_E_INVALID;
+  if (write && (!center_xyz || !radius || !material || !albedo_rgb || !fuzz || !ior)) return rtclj_fail(RTCLJ_E_INVALID, "scene_random_field: null output array");
   int n = 0;
   bool overflow = false;
   auto put = [&](double cx, double cy, double cz, double r, int kind, double ar, double ag, double ab, double fz,

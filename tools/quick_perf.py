@@ -19,6 +19,12 @@ def peaks():
 
 
 def run(name, world, cam, spp, depth, flags, reps=3, **kw):
+    if os.environ.get("RTCLJ_QP_LANE"):
+        flags |= _abi.F_LANE_KERNEL
+        name += "[lane-kernel]"
+    if os.environ.get("RTCLJ_QP_STRICT"):
+        kw["samples_per_unit"] = spp
+        name += "[strict]"
     ctx = render.Context(0)
     ctx.set_scene(world)
     out = torch.zeros((cam.height, cam.width, 3), dtype=torch.float64, device="cuda:0")
@@ -49,6 +55,8 @@ if __name__ == "__main__":
         "cover_1920x1080x16": lambda: (cover, CAM.main_camera(1920, 1080, **S.COVER_CAMERA), 16),
         "cover_normalshade_1920x1080x32": lambda: (cover, CAM.main_camera(1920, 1080, **S.COVER_CAMERA), 32, _abi.FLAGS_I),
         "default_1920x1080x16": lambda: (S.main_hittables(), CAM.main_camera(1920), 16),
+        "realm_1920x1080x16": lambda: (S.realm_hittables(), CAM.realm_camera(1920), 16, _abi.FLAGS_REALM),
+        "i_3840x2160x16": lambda: (S.i_hittables(), CAM.i_camera(3840), 16, _abi.FLAGS_I),
         "field10k_960x540x4": lambda: (S.field_hittables(7), CAM.main_camera(960, 540, **S.FIELD_CAMERA), 4),
     }
     if not only:
