@@ -1,0 +1,71 @@
+"""Properties of the built sm_100a code that the design depends on and that a compiler or source change
+can silently break (checked on the CPU box with cuobjdump)."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "raytracing-clj_b200", "librtclj_b200.so")
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not installed")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    out = subprocess.run(["cuobjdump", "-sass", LIB], check=True, capture_output=True, text=True).stdout
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s", line):
+            funcs[name].append(line)
+    return funcs
+
+
+def kernel(funcs, key):
+    names = [n for n in funcs if key in n]
+    assert len(names) == 1, names
+    return funcs[names[0]]
+
+
+def test_only_sm_100a_code_is_shipped():
+    out = subprocess.run(["cuobjdump", "-lelf", LIB], check=True, capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.parametrize("key", ["render_wave_kernel", "render_kernelILb1"])
+def test_small_scene_cull_takes_its_table_through_uniform_registers(sass, key):
+    """<= 512 spheres: the cull table is a kernel parameter and must reach FFMA2 as UNIFORM operands
+    (LDCU.64 UR, c[0x0][UR+..] -> FFMA2 R, R.F32, UR.F32x2, ..).  ptxas silently falls back to per-lane LDC
+    when it cannot prove the warp converged (e.g. after a spin-wait without __syncwarp), which costs ~12 %."""
+    body = kernel(sass, key)
+    uniform = [l for l in body if re.search(r"LDCU\.64 UR\d+, c\[0x0\]\[UR\d+", l)]
+    per_lane = [l for l in body if re.search(r"LDC\.64 R\d+, c\[0x0\]\[R\d+", l)]
+    assert len(uniform) >= 32 and not per_lane, (len(uniform), len(per_lane))
+    assert sum("FFMA2" in l and ".F32x2" in l and " UR" in l for l in body) >= 48
+
+
+def test_large_scene_table_is_staged_by_tma(sass):
+    body = kernel(sass, "render_kernelILb0")
+    assert any("UBLKCP" in l for l in body) and any("SYNCS" in l for l in body)
+
+
+def test_no_module_global_constant_table():
+    """The round-1 __constant__ cull table (shared by every context of a device) is gone."""
+    out = subprocess.run(["cuobjdump", "-elf", LIB], check=True, capture_output=True, text=True).stdout
+    assert "g_ctab" not in out
+    assert not re.search(r"\.nv\.constant3", out)
+
+
+def test_wave_kernel_fits_the_instruction_cache_budget(sass):
+    """59 KB of SASS stalled 5.5 warps per issue on instruction fetch (profiles/r2_wave_v1_*): keep the
+    kernel's resident body under 32 KB and the whole function under 48 KB."""
+    body = kernel(sass, "render_wave_kernel")
+    first_exit = next(i for i, l in enumerate(body) if re.search(r"\bEXIT\b", l))
+    assert len(body) * 16 <= 48 * 1024, len(body) * 16
+    assert first_exit * 16 <= 32 * 1024, first_exit * 16
