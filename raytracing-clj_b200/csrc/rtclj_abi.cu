@@ -4,6 +4,7 @@
 #include "../../include/rtclj_b200.h"
 #include "rtclj_kernels.cuh"
 #include "rtclj_wave_kernel.cuh"
+#include "rtclj_lane2_kernel.cuh"
 #include "rtclj_p3_kernels.cuh"
 #include "rtclj_error.h"
 
@@ -21,6 +22,10 @@
 #include <vector>
 
 using namespace rtclj;
+
+#ifndef RTCLJ_DEFAULT_SMALL_KERNEL
+#define RTCLJ_DEFAULT_SMALL_KERNEL SMALL_LANE2
+#endif
 
 namespace {
 
@@ -237,6 +242,7 @@ int rtclj_ctx_create(int32_t device, rtclj_ctx** out) {
   CU(cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   CU(cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   CU(cudaFuncSetAttribute(render_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WaveSmem::total));
+  CU(cudaFuncSetAttribute(render_lane2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lane2Smem::total));
   *out = guard.release();
   return RTCLJ_OK;
 }
@@ -386,8 +392,15 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   const int grid = c->sm_count;
   const bool run_kernel = prm->max_depth > 0;
   const bool const_tab = use_const_table(c->nhalf) && !(prm->flags & RTCLJ_F_SMEM_TABLE);
-  // scenes of <= 512 spheres: the wavefront kernel, which also finishes the pixels itself
-  const bool wave = run_kernel && const_tab && !(prm->flags & RTCLJ_F_LANE_KERNEL);
+  // scenes of <= 512 spheres: three kernels produce the same image (tests); the default is the fastest
+  // measured on the bench workload, the flags select the others for A/B timing
+  enum { SMALL_LANE1, SMALL_LANE2, SMALL_WAVE };
+  int small = RTCLJ_DEFAULT_SMALL_KERNEL;
+  if (prm->flags & RTCLJ_F_LANE_KERNEL) small = SMALL_LANE1;
+  if (prm->flags & RTCLJ_F_LANE2_KERNEL) small = SMALL_LANE2;
+  if (prm->flags & RTCLJ_F_WAVE_KERNEL) small = SMALL_WAVE;
+  const bool wave = run_kernel && const_tab && small == SMALL_WAVE;    // also finishes the pixels itself
+  const bool lane2 = run_kernel && const_tab && small == SMALL_LANE2;
   const bool want_out = d_out_linear || d_out_rgb8;
   if (!wave || nchunks > 1) CU(c->partial.reserve((size_t)total_units * 3));
   CU(cudaEventRecord(c->ev0, stream));
@@ -427,6 +440,13 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
         P.arrive = c->arrive.p;
       }
       render_wave_kernel<<<grid, kWT, WaveSmem::total, stream>>>(P);
+    } else if (lane2) {
+      P.stack_stride = (unsigned)grid * (unsigned)kT2 * 2u;
+      if (prm->max_depth > 1) {
+        CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
+        P.stack = c->stack.p;
+      }
+      render_lane2_kernel<<<grid, kT2, Lane2Smem::total, stream>>>(P);
     } else {
       P.stack_stride = (unsigned)grid * (unsigned)threads_of(const_tab);
       if (prm->flags & RTCLJ_F_REVERSE_PRODUCT) {

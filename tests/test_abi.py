@@ -84,3 +84,16 @@ def test_header_is_valid_c11_and_host_entry_points_work_from_c(tmp_path):
     import subprocess
     out = subprocess.run([build_c_client(tmp_path)], check=True, capture_output=True, text=True).stdout
     assert out.strip() == "ok host"
+
+
+def test_every_entry_point_describes_its_error():
+    """rtclj_last_error() after a failing HOST-side call (those returned bare codes)."""
+    from raytracing_clj_b200 import _abi
+    lib = _abi.lib()
+    n = C.c_size_t()
+    for call in (lambda: lib.rtclj_encode_ppm_p3(None, 0, 0, None, 0, C.byref(n)),
+                 lambda: lib.rtclj_decode_ppm_p3(b"P6\n1 1\n255\n", 11, C.byref(C.c_int32()), C.byref(C.c_int32()), None, 0),
+                 lambda: lib.rtclj_camera_i(0, 0, None),
+                 lambda: lib.rtclj_quantise_rgb8(None, 3, 0, None)):
+        rc = call()
+        assert rc != 0 and lib.rtclj_last_error().decode() != ""

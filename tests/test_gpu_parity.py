@@ -22,8 +22,8 @@ def gpu(world, cam, spp, depth, **kw):
 
 def assert_same(world, cam, spp, depth, seed, flags, unit=0, threads=8, **kw):
     soa = S.to_soa(world)
-    lin_o, rgb_o, st_o = O.render(soa, cam, spp, depth, seed=seed, flags=flags, threads=threads,
-                                  samples_per_unit=unit if unit else spp)
+    lin_o, rgb_o, st_o = O.render(soa, cam, spp, depth, seed=seed, flags=flags & 0xffff, threads=threads,
+                                  samples_per_unit=unit if unit else spp)   # the high bits select GPU code paths
     lin_g, rgb_g, st_g = gpu(soa, cam, spp, depth, seed=seed, flags=flags,
                              samples_per_unit=unit if unit else spp, **kw)
     bad = np.argwhere(lin_o != lin_g)
@@ -154,6 +154,54 @@ def test_both_kernels_agree_with_the_oracle():
             lin_g, rgb_g, st_g = gpu(soa, cam, 8, 50, seed=seed, flags=flags | extra, samples_per_unit=8)
             assert np.array_equal(lin_o, lin_g) and np.array_equal(rgb_o, rgb_g), extra
             assert st_g["segments"] == st_o.segments
+
+
+SMALL_KERNELS = {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL}
+
+
+@pytest.mark.parametrize("which", sorted(SMALL_KERNELS))
+def test_every_small_scene_kernel_agrees_with_the_oracle(which):
+    """Scenes of <= 512 spheres have three kernels (one path per lane, two paths per lane, wavefront);
+    the library picks one, the RTCLJ_F_*_KERNEL flags select each.  All of them against the oracle:
+    every variant, defocus, glass, depth caps (attenuation stack, K_END), chunked units, ragged sizes,
+    exact ties, an empty list, shards, and the device-resident call."""
+    extra = SMALL_KERNELS[which]
+    sp, mat = R.hittable.sphere, R.material
+    walls = [S.body(sp((0, 0, 0), 50.0), mat.metal((0.99, 0.98, 0.97), 0.0)),
+             S.body(sp((0, 0, -1), 0.5), mat.dielectric(1.5)),
+             S.body(sp((1.2, 0, -1), 0.5), mat.lambertian((0.5, 0.5, 0.9)))]
+    tie = [S.body(sp((0, 0, -1), 0.5), mat.lambertian((0.9, 0.1, 0.1))),
+           S.body(sp((0, 0, -1), 0.5), mat.lambertian((0.1, 0.9, 0.1)))]
+    cases = [
+        (S.cover_hittables(7), CAM.main_camera(160, 90, **S.COVER_CAMERA), 8, 50, 7, O.FLAGS_MAIN, 0),
+        (S.cover_hittables(11), CAM.realm_camera(120, 67, look_from=(13.0, 2.0, 3.0), look_at=(0.0, 0.0, 0.0)), 9, 50, 22, O.FLAGS_REALM, 4),
+        (S.main_hittables(), CAM.main_camera(200), 32, 50, 1, O.FLAGS_MAIN, 7),
+        (S.realm_hittables(), CAM.realm_camera(200), 32, 50, 2, O.FLAGS_REALM, 0),
+        (S.i_hittables(), CAM.i_camera(200), 16, 50, 3, O.FLAGS_I, 0),
+        (S.realm_hittables(), CAM.i_camera(64), 4, 1, 2, O.FLAGS_REALM, 0),
+        (S.cover_hittables(2)[:7], CAM.main_camera(37, 23, **S.COVER_CAMERA), 7, 50, 5, O.FLAGS_MAIN, 3),
+        (tie, CAM.i_camera(48), 4, 50, 1, O.FLAGS_REALM, 0),
+        ([], CAM.realm_camera(32), 4, 50, 1, O.FLAGS_REALM, 0),
+        (S.cover_hittables(9)[:17], CAM.main_camera(1, 40, **S.COVER_CAMERA), 5, 50, 6, O.FLAGS_MAIN, 2),
+    ]
+    for depth in (1, 2, 7, 120):
+        cases.append((walls, CAM.i_camera(40), 4, depth, 3, O.FLAGS_MAIN, 0))
+        cases.append((walls, CAM.i_camera(40), 4, depth, 3, O.FLAGS_REALM, 0))
+    for world, cam, spp, depth, seed, flags, unit in cases:
+        st = assert_same(world, cam, spp, depth, seed, flags | extra, unit=unit)
+    # shards: the union of the shards' rows is the whole image
+    world, cam = S.main_hittables(), CAM.main_camera(96)
+    whole, rgb_whole, st = gpu(world, cam, 8, 50, seed=5, samples_per_unit=4, flags=O.FLAGS_MAIN | extra)
+    lin = np.zeros_like(whole); rgb = np.zeros_like(rgb_whole); segs = 0
+    for idx in range(3):
+        _, _, s1 = gpu(world, cam, 8, 50, seed=5, samples_per_unit=4, flags=O.FLAGS_MAIN | extra, shard=(idx, 3, 5),
+                       out_linear=lin, out_rgb8=rgb)
+        segs += s1["segments"]
+    assert np.array_equal(lin, whole) and np.array_equal(rgb, rgb_whole) and segs == st["segments"]
+    # cull == exhaustive fp64 scan
+    a, ra, sa = gpu(S.cover_hittables(3), CAM.main_camera(96, 54, **S.COVER_CAMERA), 6, 50, seed=9, flags=O.FLAGS_MAIN | extra, samples_per_unit=6)
+    b, rb, sb = gpu(S.cover_hittables(3), CAM.main_camera(96, 54, **S.COVER_CAMERA), 6, 50, seed=9, flags=O.FLAGS_MAIN | extra | _abi.F_NO_CULL, samples_per_unit=6)
+    assert np.array_equal(a, b) and np.array_equal(ra, rb) and sa["segments"] == sb["segments"]
 
 
 def test_block_boundaries_and_kernel_switch():
@@ -323,18 +371,6 @@ def test_extreme_image_shapes():
     lin_o, rgb_o, st_o = O.render(soa, small, 4000, 50, seed=6, flags=O.FLAGS_MAIN, threads=8,
                                   samples_per_unit=st_g["samples_per_unit"])
     assert np.array_equal(lin_o, lin_g) and np.array_equal(rgb_o, rgb_g) and st_g["segments"] == st_o.segments
-
-
-def test_multi_device_equals_single_device():
-    import ctypes as C
-    n = C.c_int()
-    _abi.check(_abi.lib().rtclj_device_count(C.byref(n)))
-    if n.value < 2:
-        pytest.skip("one GPU on this box")
-    world, cam = S.cover_hittables(7), CAM.main_camera(192, 108, **S.COVER_CAMERA)
-    a, ra, sa = gpu(world, cam, 8, 50, seed=2, devices=[0])
-    b, rb, sb = gpu(world, cam, 8, 50, seed=2, devices=list(range(n.value)))
-    assert np.array_equal(a, b) and np.array_equal(ra, rb) and sa["segments"] == sb["segments"]
 
 
 def test_device_resident_context_matches_host_call():
