@@ -285,11 +285,14 @@ def main():
         with open(shm_path, "wb") as f:
             f.truncate(lin_bytes + rgb_bytes)
     barrier()
-    host_lin = np.memmap(shm_path, dtype=np.float64, mode="r+", offset=0, shape=(H, W, 3))
-    host_rgb = np.memmap(shm_path, dtype=np.uint8, mode="r+", offset=lin_bytes, shape=(H, W, 3))
-    host_lin[:] = 0  # touch the pages, then pin the shared mapping once (outside the timed region)
-    host_rgb[:] = 0
-    pinned = lib.rtclj_host_register(C.c_void_p(host_lin.ctypes.data), lin_bytes + rgb_bytes) == 0
+    whole = np.memmap(shm_path, dtype=np.uint8, mode="r+", shape=(lin_bytes + rgb_bytes,))  # ONE mapping, shared by the ranks
+    host_lin = whole[:lin_bytes].view(np.float64).reshape(H, W, 3)
+    host_rgb = whole[lin_bytes:].reshape(H, W, 3)
+    whole[:] = 0  # touch the pages, then pin the mapping once (outside the timed region)
+    pinned = lib.rtclj_host_register(C.c_void_p(whole.ctypes.data), lin_bytes + rgb_bytes) == 0
+    if not pinned:
+        print("bench: rtclj_host_register failed (%s): e2e goes through the library's staging copy"
+              % lib.rtclj_last_error().decode(), file=sys.stderr)
 
     def e2e_step():
         return render.render(soa, cam, spp, depth, seed=1, flags=flags, shard=shard,
@@ -330,7 +333,7 @@ def main():
                   "note": "rank 0 alone calls rtclj_render_multi over all GPUs (one worker thread per device)"}
     barrier()
     if pinned:
-        lib.rtclj_host_unregister(C.c_void_p(host_lin.ctypes.data))
+        lib.rtclj_host_unregister(C.c_void_p(whole.ctypes.data))
     if rank == 0:
         try:
             os.unlink(shm_path)

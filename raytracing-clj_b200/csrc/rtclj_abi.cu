@@ -23,9 +23,6 @@
 
 using namespace rtclj;
 
-#ifndef RTCLJ_DEFAULT_SMALL_KERNEL
-#define RTCLJ_DEFAULT_SMALL_KERNEL SMALL_LANE2
-#endif
 
 namespace {
 
@@ -395,7 +392,14 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   // scenes of <= 512 spheres: three kernels produce the same image (tests); the default is the fastest
   // measured on the bench workload, the flags select the others for A/B timing
   enum { SMALL_LANE1, SMALL_LANE2, SMALL_WAVE };
-  int small = RTCLJ_DEFAULT_SMALL_KERNEL;
+  // Two paths per lane pay when the cull dominates (many spheres) and the render is long enough to hide
+  // the longer tail of twice as many work units in flight: measured on a B200 (profiles/r2_kernel_ab.md),
+  // cover scene 1920x1080: 500 spp 543.7 vs 561.6 ms, 16 spp 19.6 vs 18.6 ms; 5 spheres: 11.7 vs 11.0 ms.
+  const double total_samples = (double)local_pixels * (double)prm->spp;
+  int small = (c->n >= 64 && total_samples >= 134217728.0) ? SMALL_LANE2 : SMALL_LANE1;
+#ifdef RTCLJ_DEFAULT_SMALL_KERNEL
+  small = RTCLJ_DEFAULT_SMALL_KERNEL;
+#endif
   if (prm->flags & RTCLJ_F_LANE_KERNEL) small = SMALL_LANE1;
   if (prm->flags & RTCLJ_F_LANE2_KERNEL) small = SMALL_LANE2;
   if (prm->flags & RTCLJ_F_WAVE_KERNEL) small = SMALL_WAVE;
