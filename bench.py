@@ -205,8 +205,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # host-side barriers: an NCCL barrier parks a spinning kernel on the GPU
 
     def barrier():
         if world_size > 1:
@@ -275,7 +277,7 @@ def main():
         s_ms, s_segs, s_k, _, s_spu = timed_device_steps(max(1, min(args.steps, 2)), samples_per_unit=spp)
         strict = {"value": s_segs * max(1, min(args.steps, 2)) / (s_ms * 1e-3), "unit": "rays/s",
                   "samples_per_unit": s_spu, "ms_per_step": s_ms / max(1, min(args.steps, 2)),
-                  "note": "samples_per_unit = spp: the reference's sequential sum per pixel (raytracing.clj:142-155)"}
+                  "note": "samples_per_unit = spp: the reference's sequential sum per pixel (raytracing.clj:142-155); per-sample colours are buffered in HBM (32 B each) and added in sample order by finalize_kernel"}
 
     # ---- e2e: host buffers through rtclj_render, H2D + D2H (into pinned host memory) inside the timed region
     soa = R.scenes.to_soa(world)
@@ -305,7 +307,13 @@ def main():
             t0 = time.perf_counter()
             if not only_rank0 or rank == 0:
                 fn()
-            barrier()
+            if only_rank0:
+                # the idle ranks must leave their GPUs FREE while rank 0 drives them: wait on the host (gloo);
+                # an NCCL barrier would keep a spinning kernel resident on every idle rank's device
+                torch.cuda.synchronize()
+                dist.barrier(group=cpu_group)
+            else:
+                barrier()
             times.append(time.perf_counter() - t0)
         t = torch.tensor(times, dtype=torch.float64, device=dev)
         if world_size > 1:

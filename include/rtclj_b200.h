@@ -181,6 +181,14 @@ int rtclj_render_multi(const rtclj_scene *scene, const rtclj_camera *camera,
                        const rtclj_params *params, const int32_t *devices, int32_t n_devices,
                        double *out_linear, uint8_t *out_rgb8, rtclj_stats *stats);
 
+/* The copies a sharded download consists of -- the host-side arithmetic behind rtclj_render (shard_*)
+ * and rtclj_render_multi, callable without a GPU.  Piece i = pieces[4i .. 4i+3] = {byte offset (the same
+ * in the device image and in the caller's image), pitch, width, height}: `height` runs of `width` bytes,
+ * `pitch` bytes apart.  max_piece_bytes = 0: the library's staging size.  pieces == NULL: count only. */
+int rtclj_shard_plan(int32_t height, size_t row_bytes, int32_t shard_index, int32_t shard_count,
+                     int32_t shard_rows, size_t max_piece_bytes, uint64_t *pieces, size_t capacity,
+                     size_t *n_pieces);
+
 /* Pinned host memory.  Output images that live in memory CUDA knows as pinned are written by the GPUs
  * directly and asynchronously; pageable images (malloc, numpy, a JVM Arena) are filled through pinned
  * staging buffers inside the library (one extra host copy).  rtclj_host_alloc returns pinned memory

@@ -85,10 +85,16 @@
             each vector a double[3].
    :devices [0 1 .. 7] interleaves the image rows over several GPUs from this one process
    (rtclj_render_multi; the reference's pool, raytracing.clj:157-171); default: GPU 0.
+   :samples-per-unit n  sums n samples sequentially per work unit.  Default 0 = the library chooses:
+   the reference's strict order (one sequential sum per pixel, raytracing.clj:142-155) for primary-ray
+   renders, whose contract is bit-exactness, and chunks of ~27 samples added in index order for
+   full-depth renders (<= 1e-13 relative difference; north_star allows 1e-3).  Pass samples-per-px
+   to force the strict order everywhere: measured on the bench workload it costs 13 % on one B200
+   and 2.2x on eight (few pixels per GPU, one 500-sample unit of tail) -- DESIGN.md section 7.
    Returns a vector of double[3] (linear RGB), row-major from the top-left pixel, i.e. `colors`
    of raytracing.clj:170-171, ready for the existing write-color! loop (:172-175)."
-  [bodies cam samples-per-px max-depth & {:keys [seed flags device devices]
-                                          :or {seed 1 flags flags-main device 0}}]
+  [bodies cam samples-per-px max-depth & {:keys [seed flags device devices samples-per-unit]
+                                          :or {seed 1 flags flags-main device 0 samples-per-unit 0}}]
   (with-open [a (Arena/ofConfined)]
     (let [n      (count bodies)
           w      (int (:image-width cam))
@@ -117,8 +123,7 @@
                    (.set ValueLayout/JAVA_INT (off :rtclj_params :max_depth) (int max-depth))
                    (.set ValueLayout/JAVA_LONG (off :rtclj_params :seed) (long seed))
                    (.set ValueLayout/JAVA_INT (off :rtclj_params :flags) (int flags))
-                   ;; the reference's summation order: one sequential sum per pixel (raytracing.clj:142-155)
-                   (.set ValueLayout/JAVA_INT (off :rtclj_params :samples_per_unit) (int samples-per-px))
+                   (.set ValueLayout/JAVA_INT (off :rtclj_params :samples_per_unit) (int samples-per-unit))
                    (.set ValueLayout/JAVA_INT (off :rtclj_params :device) (int device)))
           [^MemorySegment out free!] (pinned-doubles a (* 3 (long w) (long h)))]
       (try

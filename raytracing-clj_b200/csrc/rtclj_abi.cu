@@ -73,6 +73,7 @@ struct rtclj_ctx {
   DevBuf<unsigned long long> counters;  // [0] queue, [1..4] stats
   DevBuf<unsigned short> stack;
   DevBuf<unsigned> arrive;              // wavefront kernel: chunk arrival counters per pixel
+  DevBuf<double> sample_buf;            // strict order on long paths: one colour per sample (kept between renders)
   std::vector<float> ctab_host;         // the cull table of a small scene: launched as a kernel parameter
   KParams kparams;                      // launch parameters of the last render (8.4 KB with the table)
   DevBuf<double> out_linear;            // used by the host-buffer entry points
@@ -236,10 +237,13 @@ int rtclj_ctx_create(int32_t device, rtclj_ctx** out) {
   CU(cudaEventCreateWithFlags(&c->pin_ev[1], cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CU(c->counters.reserve(8));
-  CU(cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-  CU(cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  CU(cudaFuncSetAttribute(render_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  CU(cudaFuncSetAttribute(render_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  CU(cudaFuncSetAttribute(render_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  CU(cudaFuncSetAttribute(render_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   CU(cudaFuncSetAttribute(render_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WaveSmem::total));
-  CU(cudaFuncSetAttribute(render_lane2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lane2Smem::total));
+  CU(cudaFuncSetAttribute(render_lane2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lane2Smem::total));
+  CU(cudaFuncSetAttribute(render_lane2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lane2Smem::total));
   *out = guard.release();
   return RTCLJ_OK;
 }
@@ -249,7 +253,7 @@ void rtclj_ctx_destroy(rtclj_ctx* c) {
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   c->geom32.release(); c->geom64.release(); c->mat.release(); c->partial.release();
-  c->counters.release(); c->stack.release(); c->arrive.release(); c->out_linear.release(); c->out_rgb8.release();
+  c->counters.release(); c->stack.release(); c->arrive.release(); c->sample_buf.release(); c->out_linear.release(); c->out_rgb8.release();
   c->p3_state.release(); c->p3_in.release(); c->p3_text.release();
   for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->p3_ev0, c->p3_ev1, c->pin_ev[0], c->pin_ev[1]})
     if (e) cudaEventDestroy(e);
@@ -369,26 +373,11 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   const int shard_index = shard_count > 1 ? prm->shard_index : 0;
   const int shard_rows = shard_count > 1 ? prm->shard_rows : H;
   const int local_rows = local_rows_of(H, shard_index, shard_count, shard_rows);
-  // Summation unit.  Primary-ray renders (max-depth 1, normal shading) are bit-exact contracts and short
-  // paths: they default to the reference's strict sequential sum (raytracing.clj:142-155,
-  // raytracing_i.clj:146-163); other renders split a pixel into chunks for load balance.
-  const bool primary_only = prm->max_depth == 1 || (prm->flags & RTCLJ_F_NORMAL_SHADING);
-  int spu = prm->samples_per_unit > 0 ? prm->samples_per_unit
-                                      : (primary_only ? prm->spp : auto_samples_per_unit(W, H, prm->spp));
-  if (spu > prm->spp) spu = prm->spp;
-  const int nchunks = (prm->spp + spu - 1) / spu;
   const unsigned long long local_pixels = (unsigned long long)local_rows * (unsigned long long)W;
-  const unsigned long long total_units = local_pixels * (unsigned long long)nchunks;
-  if (total_units > 0xffffffffull)
-    return fail(RTCLJ_E_INVALID, "%llu work units: raise samples_per_unit", total_units);
-  c->last_spu = spu;
-
-  CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), stream));
-  if (total_units == 0) return RTCLJ_OK;
-
   const int grid = c->sm_count;
   const bool run_kernel = prm->max_depth > 0;
   const bool const_tab = use_const_table(c->nhalf) && !(prm->flags & RTCLJ_F_SMEM_TABLE);
+  const bool want_out = d_out_linear || d_out_rgb8;
   // scenes of <= 512 spheres: three kernels produce the same image (tests); the default is the fastest
   // measured on the bench workload, the flags select the others for A/B timing
   enum { SMALL_LANE1, SMALL_LANE2, SMALL_WAVE };
@@ -405,8 +394,46 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   if (prm->flags & RTCLJ_F_WAVE_KERNEL) small = SMALL_WAVE;
   const bool wave = run_kernel && const_tab && small == SMALL_WAVE;    // also finishes the pixels itself
   const bool lane2 = run_kernel && const_tab && small == SMALL_LANE2;
-  const bool want_out = d_out_linear || d_out_rgb8;
-  if (!wave || nchunks > 1) CU(c->partial.reserve((size_t)total_units * 3));
+
+  // Summation unit.  Primary-ray renders (max-depth 1, normal shading) are bit-exact contracts and short
+  // paths: they default to the reference's strict sequential sum (raytracing.clj:142-155,
+  // raytracing_i.clj:146-163); other renders split a pixel into chunks for load balance.
+  const bool primary_only = prm->max_depth == 1 || (prm->flags & RTCLJ_F_NORMAL_SHADING);
+  int spu = prm->samples_per_unit > 0 ? prm->samples_per_unit
+                                      : (primary_only ? prm->spp : auto_samples_per_unit(W, H, prm->spp));
+  if (spu > prm->spp) spu = prm->spp;
+  c->last_spu = spu;
+  // The strict order on long paths: one 500-sample unit lasts as long as its pixel's paths, the last ones
+  // run alone (measured: 622 vs 543 ms on one GPU, 162 vs 72 ms per GPU on eight).  Instead the samples are
+  // traced in small units and each sample's colour is STORED (32 B); finalize_kernel then adds them in
+  // sample order -- the same additions in the same order.  33 GB at 1920x1080 x 500 spp; HBM has 180 GB.
+  double* sample_buf = nullptr;
+  if (spu == prm->spp && !primary_only && prm->spp >= 64 && run_kernel && !wave && want_out && local_pixels > 0) {
+    const size_t need = (size_t)local_pixels * (size_t)prm->spp * 4u;  // doubles
+    size_t free_b = 0, total_b = 0;
+    // kept in the context between renders (allocating 33 GB per frame costs more than the frame); a render
+    // that does not need it gives a large one back (below)
+    if (need <= c->sample_buf.cap ||
+        (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need * 8 < (free_b + c->sample_buf.cap * 8) / 2 &&
+         c->sample_buf.reserve(need) == cudaSuccess)) {
+      sample_buf = c->sample_buf.p;
+      spu = auto_samples_per_unit(W, H, prm->spp);  // scheduling units; the arithmetic stays strict
+    } else {
+      cudaGetLastError();  // too large: fall back to one unit per pixel
+    }
+  } else if (c->sample_buf.cap * 8 > ((size_t)1 << 30)) {
+    c->sample_buf.release();  // (synchronises the device; only on a strict -> chunked change of mode)
+  }
+  const int nchunks = (prm->spp + spu - 1) / spu;
+  const unsigned long long total_units = local_pixels * (unsigned long long)nchunks;
+  if (total_units > 0xffffffffull) {
+    return fail(RTCLJ_E_INVALID, "%llu work units: raise samples_per_unit", total_units);
+  }
+
+  CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), stream));
+  if (total_units == 0) return RTCLJ_OK;
+
+  if ((!wave || nchunks > 1) && !sample_buf) CU(c->partial.reserve((size_t)total_units * 3));
   CU(cudaEventRecord(c->ev0, stream));
   if (!run_kernel) {
     CU(cudaMemsetAsync(c->partial.p, 0, (size_t)total_units * 3 * sizeof(double), stream));  // depth <= 0: black
@@ -429,6 +456,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
     P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
     P.partial = c->partial.p; P.queue = c->counters.p; P.stats = c->counters.p + 1;
+    P.sample_buf = sample_buf; P.sample_stride = local_pixels;
     if (const_tab && !c->ctab_host.empty())
       std::memcpy(P.ctab, c->ctab_host.data(), std::min(sizeof P.ctab, c->ctab_host.size() * sizeof(float)));
     if (wave) {
@@ -450,23 +478,26 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
         CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
         P.stack = c->stack.p;
       }
-      render_lane2_kernel<<<grid, kT2, Lane2Smem::total, stream>>>(P);
+      if (sample_buf) render_lane2_kernel<true><<<grid, kT2, Lane2Smem::total, stream>>>(P);
+      else render_lane2_kernel<false><<<grid, kT2, Lane2Smem::total, stream>>>(P);
     } else {
       P.stack_stride = (unsigned)grid * (unsigned)threads_of(const_tab);
       if (prm->flags & RTCLJ_F_REVERSE_PRODUCT) {
         CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
         P.stack = c->stack.p;
       }
-      if (const_tab)
-        render_kernel<true><<<grid, threads_of(true), smem_needed(c->nhalf, true, c->smem_optin), stream>>>(P);
-      else
-        render_kernel<false><<<grid, threads_of(false), smem_needed(c->nhalf, false, c->smem_optin), stream>>>(P);
+      const size_t sm = smem_needed(c->nhalf, const_tab, c->smem_optin);
+      if (const_tab && sample_buf) render_kernel<true, true><<<grid, threads_of(true), sm, stream>>>(P);
+      else if (const_tab) render_kernel<true, false><<<grid, threads_of(true), sm, stream>>>(P);
+      else if (sample_buf) render_kernel<false, true><<<grid, threads_of(false), sm, stream>>>(P);
+      else render_kernel<false, false><<<grid, threads_of(false), sm, stream>>>(P);
     }
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(c->ev1, stream));
   if (!wave && want_out) {
     FParams F;
+    F.sample_buf = sample_buf; F.sample_stride = local_pixels;
     F.partial = c->partial.p; F.out_linear = (double*)d_out_linear; F.out_rgb8 = (unsigned char*)d_out_rgb8;
     F.W = W; F.spp = prm->spp; F.nchunks = nchunks;
     F.shard_index = shard_index; F.shard_count = shard_count; F.shard_rows = shard_rows;
@@ -726,6 +757,27 @@ int rtclj_render(const rtclj_scene* scene, const rtclj_camera* cam, const rtclj_
     rc = render_shard_hostbuf(scene, cam, prm, out_linear, out_rgb8, stats);
     if (rc == RTCLJ_OK && stats) stats->n_devices = 1;
     return rc;
+  });
+}
+
+// The copies a shard's download consists of (host logic shared by rtclj_render / rtclj_render_multi),
+// exposed so that the N > 1 arithmetic is testable without a GPU.
+int rtclj_shard_plan(int32_t height, size_t row_bytes, int32_t shard_index, int32_t shard_count, int32_t shard_rows,
+                     size_t max_piece_bytes, uint64_t* pieces, size_t capacity, size_t* n_pieces) {
+  return guarded([&]() -> int {
+    if (!n_pieces) return fail(RTCLJ_E_INVALID, "null n_pieces");
+    if (height <= 0 || row_bytes == 0) return fail(RTCLJ_E_INVALID, "image size must be positive");
+    if (shard_count > 1 && (shard_index < 0 || shard_index >= shard_count || shard_rows <= 0))
+      return fail(RTCLJ_E_INVALID, "bad shard (%d of %d, %d rows)", shard_index, shard_count, shard_rows);
+    std::vector<Piece> v;
+    plan_pieces((size_t)height, row_bytes, shard_index, shard_count, shard_rows, max_piece_bytes ? max_piece_bytes : kStageBytes, v);
+    *n_pieces = v.size();
+    if (!pieces) return RTCLJ_OK;
+    if (capacity < v.size()) return fail(RTCLJ_E_BUFFER, "%zu pieces, capacity %zu", v.size(), capacity);
+    for (size_t i = 0; i < v.size(); ++i) {
+      pieces[4 * i] = v[i].off; pieces[4 * i + 1] = v[i].pitch; pieces[4 * i + 2] = v[i].width; pieces[4 * i + 3] = v[i].height;
+    }
+    return RTCLJ_OK;
   });
 }
 

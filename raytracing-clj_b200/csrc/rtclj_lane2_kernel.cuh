@@ -59,6 +59,7 @@ __device__ __forceinline__ RayView make_view(const KParams& P, d3 O, d3 D) {
 
 enum { PS_FRESH = 0, PS_RAY = 1, PS_DEAD = 2 };  // a path: needs a work unit / carries a ray / has run out of work
 
+template <bool kSampleBuf>  // strict order through the per-sample buffer: its own instantiation (rtclj_kernels.cuh)
 __global__ void __launch_bounds__(kT2, 1) render_lane2_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -316,15 +317,20 @@ __global__ void __launch_bounds__(kT2, 1) render_lane2_kernel(const __grid_const
           depth_left--;
         }
         if (done) {
-          const double sum_r = sums[0] + color.x, sum_g = sums[kT2] + color.y, sum_b = sums[2 * kT2] + color.z;  // raytracing.clj:153
-          sums[0] = sum_r; sums[kT2] = sum_g; sums[2 * kT2] = sum_b;
           status = PS_FRESH;  // no ray until the camera gives it one
-          if (++k == k_end) {
-            double* out = P.partial + (size_t)unit * 3u;
-            out[0] = sum_r; out[1] = sum_g; out[2] = sum_b;
-            need_unit = true;
+          if (kSampleBuf) {  // strict order: the sample's colour is stored, finalize_kernel adds in sample order
+            store_sample(P, unit, k, color);
+            if (++k == k_end) need_unit = true; else need_cam = true;
           } else {
-            need_cam = true;
+            const double sum_r = sums[0] + color.x, sum_g = sums[kT2] + color.y, sum_b = sums[2 * kT2] + color.z;  // raytracing.clj:153
+            sums[0] = sum_r; sums[kT2] = sum_g; sums[2 * kT2] = sum_b;
+            if (++k == k_end) {
+              double* out = P.partial + (size_t)unit * 3u;
+              out[0] = sum_r; out[1] = sum_g; out[2] = sum_b;
+              need_unit = true;
+            } else {
+              need_cam = true;
+            }
           }
         }
       }

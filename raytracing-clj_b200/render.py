@@ -27,6 +27,17 @@ def shard_rows(height: int, index: int, count: int, rows: int) -> List[int]:
     return out
 
 
+def shard_plan(height: int, row_bytes: int, index: int, count: int, rows: int, max_piece_bytes: int = 0):
+    """The copies the LIBRARY issues to download one shard (rtclj_shard_plan): a list of
+    (byte offset, pitch, width, height) -- `height` runs of `width` bytes, `pitch` apart."""
+    lib = _abi.lib()
+    n = C.c_size_t()
+    _abi.check(lib.rtclj_shard_plan(height, row_bytes, index, count, rows, max_piece_bytes, None, 0, C.byref(n)))
+    buf = (C.c_uint64 * (4 * max(1, n.value)))()
+    _abi.check(lib.rtclj_shard_plan(height, row_bytes, index, count, rows, max_piece_bytes, buf, n.value, C.byref(n)))
+    return [tuple(int(buf[4 * i + k]) for k in range(4)) for i in range(n.value)]
+
+
 def _scene_struct(soa):
     center, radius, kind, albedo, fuzz, ior = soa
     s = _abi.Scene(len(radius), 0, center.ctypes.data, radius.ctypes.data, kind.ctypes.data,

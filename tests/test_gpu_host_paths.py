@@ -146,3 +146,24 @@ def test_pinned_caller_buffers_are_written_directly_and_equal_pageable_ones():
         assert np.array_equal(buf, lin_p)
     finally:
         _abi.check(lib.rtclj_host_unregister(C.c_void_p(buf.ctypes.data)))
+
+
+@pytest.mark.parametrize("extra", [_abi.F_LANE_KERNEL, _abi.F_LANE2_KERNEL, _abi.F_SMEM_TABLE, _abi.F_WAVE_KERNEL])
+def test_strict_order_on_long_paths_goes_through_the_sample_buffer(extra):
+    """samples_per_unit >= spp on a full-depth render of >= 64 spp: the samples are traced in small units,
+    every sample's colour is stored and finalize_kernel adds them in sample order -- bit for bit the
+    reference's sequential sum (src/raytracing.clj:142-155), i.e. the oracle in strict mode.  (The wavefront
+    kernel keeps one unit per pixel.)  Also sharded, ragged, and in realm's x (1/spp) form."""
+    for world, cam, spp, flags, seed in ((S.main_hittables(), CAM.main_camera(96), 64, O.FLAGS_MAIN, 5),
+                                         (S.cover_hittables(7), CAM.main_camera(64, 36, **S.COVER_CAMERA), 70, O.FLAGS_MAIN, 6),
+                                         (S.realm_hittables(), CAM.realm_camera(37), 65, O.FLAGS_REALM, 7)):
+        soa = S.to_soa(world)
+        lin_o, rgb_o, st_o = O.render(soa, cam, spp, 50, seed=seed, flags=flags, threads=8, samples_per_unit=spp)
+        lin_g, rgb_g, st_g = render.render(soa, cam, spp, 50, seed=seed, flags=flags | extra, samples_per_unit=spp)
+        assert st_g["samples_per_unit"] == spp and st_g["segments"] == st_o.segments
+        assert np.array_equal(lin_o, lin_g) and np.array_equal(rgb_o, rgb_g)
+        lin = np.zeros_like(lin_g)
+        for idx in range(3):
+            render.render(soa, cam, spp, 50, seed=seed, flags=flags | extra, samples_per_unit=spp, shard=(idx, 3, 2),
+                          out_linear=lin, want_rgb8=False)
+        assert np.array_equal(lin, lin_o)

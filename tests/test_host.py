@@ -197,3 +197,28 @@ def test_shard_rows_partition_the_image():
             seen += render.shard_rows(H, i, count, rows)
         assert sorted(seen) == list(range(H))
     assert render.shard_rows(20, 1, 2, 4) == [4, 5, 6, 7, 12, 13, 14, 15]
+
+
+def test_shard_plan_covers_exactly_the_shards_rows():
+    """The library's download plan (C++, rtclj_shard_plan) against the Python shard arithmetic: for every
+    shard the planned byte runs are exactly the shard's rows -- no byte twice, none missing, none foreign --
+    for ragged last tiles, tiles larger than a staging piece, more shards than tiles, and no sharding."""
+    from raytracing_clj_b200 import render
+    for H, row_bytes, count, rows, cap in ((225, 96, 2, 4, 0), (135, 64, 8, 1, 0), (37, 1000, 3, 5, 4096),
+                                           (50, 4096, 4, 16, 10000), (7, 64, 16, 1, 0), (100, 24, 1, 0, 512),
+                                           (2160, 48, 8, 1, 16 << 20), (13, 100, 5, 3, 250)):
+        seen = np.zeros(H * row_bytes, dtype=np.int32)
+        for idx in range(max(1, count)):
+            mine = np.zeros(H * row_bytes, dtype=np.int32)
+            for off, pitch, width, height in render.shard_plan(H, row_bytes, idx, count, rows, cap):
+                assert 0 < width * height <= (cap or (16 << 20))
+                for r in range(height):
+                    a = off + r * pitch
+                    assert a + width <= H * row_bytes
+                    mine[a:a + width] += 1
+            want = np.zeros(H * row_bytes, dtype=np.int32)
+            for j in render.shard_rows(H, idx, count, rows):
+                want[j * row_bytes:(j + 1) * row_bytes] = 1
+            assert np.array_equal(mine, want), (H, row_bytes, idx, count, rows)   # each byte of the shard exactly once
+            seen += mine
+        assert np.all(seen == 1), "the shards partition the image"
