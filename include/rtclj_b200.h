@@ -12,6 +12,8 @@
  *                           realm[0 .. 3*W*H)), and
  *                           src/experimental/raytracing_i.clj:146-163
  *   rtclj_render_multi      the same loop, image rows interleaved over several GPUs
+ *   rtclj_render_multi_ppm  the same loop followed by the write-color! loop (raytracing.clj:172-175):
+ *                           several GPUs in, the text of scene.ppm out
  *   rtclj_ctx_*             the same loop with device-resident buffers (scene upload
  *                           once, many renders; what bench.py times as `value`)
  *   rtclj_quantise_rgb8     write-color! / linear->gamma / clamp,
@@ -180,6 +182,15 @@ int rtclj_render(const rtclj_scene *scene, const rtclj_camera *camera,
 int rtclj_render_multi(const rtclj_scene *scene, const rtclj_camera *camera,
                        const rtclj_params *params, const int32_t *devices, int32_t n_devices,
                        double *out_linear, uint8_t *out_rgb8, rtclj_stats *stats);
+
+/* The render loop AND the write-color! loop (src/raytracing.clj:141-175) as one call: renders on
+ * `n_devices` GPUs (n_devices = 1 is fine), assembles the 8-bit shards on devices[0] by device-to-device
+ * copies, runs the device P3 writer there and returns the text of the PPM file -- the bytes
+ * rtclj_encode_ppm_p3 would produce from rtclj_render's rgb8 image; only the text crosses PCIe.
+ * out == NULL: *len receives a sufficient capacity (an upper bound; nothing is rendered). */
+int rtclj_render_multi_ppm(const rtclj_scene *scene, const rtclj_camera *camera,
+                           const rtclj_params *params, const int32_t *devices, int32_t n_devices,
+                           char *out, size_t capacity, size_t *len, rtclj_stats *stats);
 
 /* The copies a sharded download consists of -- the host-side arithmetic behind rtclj_render (shard_*)
  * and rtclj_render_multi, callable without a GPU.  Piece i = pieces[4i .. 4i+3] = {byte offset (the same

@@ -47,6 +47,14 @@
   (downcall "rtclj_render_multi"
             (fd-int ValueLayout/ADDRESS ValueLayout/ADDRESS ValueLayout/ADDRESS ValueLayout/ADDRESS
                     ValueLayout/JAVA_INT ValueLayout/ADDRESS ValueLayout/ADDRESS ValueLayout/ADDRESS)))
+;; int rtclj_render_multi_ppm(const rtclj_scene*, const rtclj_camera*, const rtclj_params*,
+;;                            const int32_t* devices, int32_t n_devices,
+;;                            char* out, size_t capacity, size_t* len, rtclj_stats*)
+(def ^:private rtclj-render-multi-ppm
+  (downcall "rtclj_render_multi_ppm"
+            (fd-int ValueLayout/ADDRESS ValueLayout/ADDRESS ValueLayout/ADDRESS ValueLayout/ADDRESS
+                    ValueLayout/JAVA_INT ValueLayout/ADDRESS ValueLayout/JAVA_LONG ValueLayout/ADDRESS
+                    ValueLayout/ADDRESS)))
 ;; int rtclj_host_alloc(size_t bytes, void** out);  int rtclj_host_free(void* p)
 (def ^:private rtclj-host-alloc (downcall "rtclj_host_alloc" (fd-int ValueLayout/JAVA_LONG ValueLayout/ADDRESS)))
 (def ^:private rtclj-host-free (downcall "rtclj_host_free" (fd-int ValueLayout/ADDRESS)))
@@ -78,6 +86,38 @@
         ^MemorySegment p (.reinterpret (.get slot ValueLayout/ADDRESS 0) (* 8 n-doubles))]
     [p #(.invokeWithArguments rtclj-host-free [p])]))
 
+(defn- marshal
+  "Fills rtclj_scene / rtclj_camera / rtclj_params in arena `a`; returns [scene camera params]."
+  [^Arena a bodies cam samples-per-px max-depth {:keys [seed flags device samples-per-unit]
+                                                 :or {seed 1 flags flags-main device 0 samples-per-unit 0}}]
+  (let [scene  (doto (.allocate a (size :rtclj_scene) 8)
+                 (.set ValueLayout/JAVA_INT (off :rtclj_scene :n) (int (count bodies)))
+                 (.set ValueLayout/ADDRESS (off :rtclj_scene :center_xyz) (doubles-seg a (mapcat :rtclj/center bodies)))
+                 (.set ValueLayout/ADDRESS (off :rtclj_scene :radius) (doubles-seg a (map :rtclj/radius bodies)))
+                 (.set ValueLayout/ADDRESS (off :rtclj_scene :material)
+                       (.allocateFrom a ValueLayout/JAVA_INT (int-array (map :rtclj/kind bodies))))
+                 (.set ValueLayout/ADDRESS (off :rtclj_scene :albedo_rgb) (doubles-seg a (mapcat :rtclj/albedo bodies)))
+                 (.set ValueLayout/ADDRESS (off :rtclj_scene :fuzz) (doubles-seg a (map :rtclj/fuzz bodies)))
+                 (.set ValueLayout/ADDRESS (off :rtclj_scene :ior) (doubles-seg a (map :rtclj/ior bodies))))
+        camera (.allocate a (size :rtclj_camera) 8)
+        put3   (fn [field ^doubles v]
+                 (dotimes [k 3]
+                   (.set camera ValueLayout/JAVA_DOUBLE (+ (off :rtclj_camera field) (* 8 k)) (aget v k))))
+        _      (do (put3 :pixel00 (:pixel-00-loc cam)) (put3 :pixel_du (:pixel-du cam))
+                   (put3 :pixel_dv (:pixel-dv cam)) (put3 :center (:camera-center cam))
+                   (put3 :defocus_u (:defocus-disk-u cam)) (put3 :defocus_v (:defocus-disk-v cam))
+                   (.set camera ValueLayout/JAVA_DOUBLE (off :rtclj_camera :defocus_angle) (double (:defocus-angle cam)))
+                   (.set camera ValueLayout/JAVA_INT (off :rtclj_camera :width) (int (:image-width cam)))
+                   (.set camera ValueLayout/JAVA_INT (off :rtclj_camera :height) (int (:image-height cam))))
+        params (doto (.allocate a (size :rtclj_params) 8)
+                 (.set ValueLayout/JAVA_INT (off :rtclj_params :spp) (int samples-per-px))
+                 (.set ValueLayout/JAVA_INT (off :rtclj_params :max_depth) (int max-depth))
+                 (.set ValueLayout/JAVA_LONG (off :rtclj_params :seed) (long seed))
+                 (.set ValueLayout/JAVA_INT (off :rtclj_params :flags) (int flags))
+                 (.set ValueLayout/JAVA_INT (off :rtclj_params :samples_per_unit) (int samples-per-unit))
+                 (.set ValueLayout/JAVA_INT (off :rtclj_params :device) (int device)))]
+    [scene camera params]))
+
 (defn render
   "bodies : hittable list made with rtclj.scene, in LIST ORDER (the first body wins a tie).
    cam    : {:pixel-00-loc :pixel-du :pixel-dv :camera-center :defocus-disk-u :defocus-disk-v
@@ -89,43 +129,16 @@
    the reference's strict order (one sequential sum per pixel, raytracing.clj:142-155) for primary-ray
    renders, whose contract is bit-exactness, and chunks of ~27 samples added in index order for
    full-depth renders (<= 1e-13 relative difference; north_star allows 1e-3).  Pass samples-per-px
-   to force the strict order everywhere: measured on the bench workload it costs 13 % on one B200
-   and 2.2x on eight (few pixels per GPU, one 500-sample unit of tail) -- DESIGN.md section 7.
+   to force the strict order everywhere: the library then buffers every sample's colour in HBM and adds
+   them in sample order, 2 % slower than chunks on one B200 and 6 % on eight -- DESIGN.md section 4.5.
    Returns a vector of double[3] (linear RGB), row-major from the top-left pixel, i.e. `colors`
    of raytracing.clj:170-171, ready for the existing write-color! loop (:172-175)."
-  [bodies cam samples-per-px max-depth & {:keys [seed flags device devices samples-per-unit]
-                                          :or {seed 1 flags flags-main device 0 samples-per-unit 0}}]
+  [bodies cam samples-per-px max-depth & {:keys [devices] :as opts}]
   (with-open [a (Arena/ofConfined)]
-    (let [n      (count bodies)
-          w      (int (:image-width cam))
-          h      (int (:image-height cam))
-          scene  (doto (.allocate a (size :rtclj_scene) 8)
-                   (.set ValueLayout/JAVA_INT (off :rtclj_scene :n) (int n))
-                   (.set ValueLayout/ADDRESS (off :rtclj_scene :center_xyz) (doubles-seg a (mapcat :rtclj/center bodies)))
-                   (.set ValueLayout/ADDRESS (off :rtclj_scene :radius) (doubles-seg a (map :rtclj/radius bodies)))
-                   (.set ValueLayout/ADDRESS (off :rtclj_scene :material)
-                         (.allocateFrom a ValueLayout/JAVA_INT (int-array (map :rtclj/kind bodies))))
-                   (.set ValueLayout/ADDRESS (off :rtclj_scene :albedo_rgb) (doubles-seg a (mapcat :rtclj/albedo bodies)))
-                   (.set ValueLayout/ADDRESS (off :rtclj_scene :fuzz) (doubles-seg a (map :rtclj/fuzz bodies)))
-                   (.set ValueLayout/ADDRESS (off :rtclj_scene :ior) (doubles-seg a (map :rtclj/ior bodies))))
-          camera (.allocate a (size :rtclj_camera) 8)
-          put3   (fn [field ^doubles v]
-                   (dotimes [k 3]
-                     (.set camera ValueLayout/JAVA_DOUBLE (+ (off :rtclj_camera field) (* 8 k)) (aget v k))))
-          _      (do (put3 :pixel00 (:pixel-00-loc cam)) (put3 :pixel_du (:pixel-du cam))
-                     (put3 :pixel_dv (:pixel-dv cam)) (put3 :center (:camera-center cam))
-                     (put3 :defocus_u (:defocus-disk-u cam)) (put3 :defocus_v (:defocus-disk-v cam))
-                     (.set camera ValueLayout/JAVA_DOUBLE (off :rtclj_camera :defocus_angle) (double (:defocus-angle cam)))
-                     (.set camera ValueLayout/JAVA_INT (off :rtclj_camera :width) w)
-                     (.set camera ValueLayout/JAVA_INT (off :rtclj_camera :height) h))
-          params (doto (.allocate a (size :rtclj_params) 8)
-                   (.set ValueLayout/JAVA_INT (off :rtclj_params :spp) (int samples-per-px))
-                   (.set ValueLayout/JAVA_INT (off :rtclj_params :max_depth) (int max-depth))
-                   (.set ValueLayout/JAVA_LONG (off :rtclj_params :seed) (long seed))
-                   (.set ValueLayout/JAVA_INT (off :rtclj_params :flags) (int flags))
-                   (.set ValueLayout/JAVA_INT (off :rtclj_params :samples_per_unit) (int samples-per-unit))
-                   (.set ValueLayout/JAVA_INT (off :rtclj_params :device) (int device)))
-          [^MemorySegment out free!] (pinned-doubles a (* 3 (long w) (long h)))]
+    (let [w      (long (:image-width cam))
+          h      (long (:image-height cam))
+          [scene camera params] (marshal a bodies cam samples-per-px max-depth opts)
+          [^MemorySegment out free!] (pinned-doubles a (* 3 w h))]
       (try
         (check!
          (if (seq devices)
@@ -139,8 +152,27 @@
                 (double-array [(.getAtIndex out ValueLayout/JAVA_DOUBLE (* 3 p))
                                (.getAtIndex out ValueLayout/JAVA_DOUBLE (+ 1 (* 3 p)))
                                (.getAtIndex out ValueLayout/JAVA_DOUBLE (+ 2 (* 3 p)))]))
-              (range (* (long w) (long h))))
+              (range (* w h)))
         (finally (free!))))))
+
+(defn render-ppm!
+  "Everything between the camera let-block and ppm->png in raytracing/-main (raytracing.clj:141-175) as ONE
+   native call: the render loop on :devices (default [0]) and the write-color! loop on the first of them;
+   the text of scene.ppm comes back and is handed to a single .write.  The image never visits the host."
+  [^String path bodies cam samples-per-px max-depth & {:keys [devices] :or {devices [0]} :as opts}]
+  (with-open [a (Arena/ofConfined)]
+    (let [w    (long (:image-width cam))
+          h    (long (:image-height cam))
+          [scene camera params] (marshal a bodies cam samples-per-px max-depth opts)
+          cap  (+ 64 (* 12 w h))                           ; "255 255 255\n" per pixel + header
+          out  (.allocate a cap 16)
+          len  (.allocate a 8 8)]
+      (check! (.invokeWithArguments rtclj-render-multi-ppm
+                                    [scene camera params
+                                     (.allocateFrom a ValueLayout/JAVA_INT (int-array devices)) (int (count devices))
+                                     out cap len MemorySegment/NULL]))
+      (with-open [o (java.io.FileOutputStream. path)]
+        (.write (.getChannel o) (.asByteBuffer (.asSlice out 0 (.get len ValueLayout/JAVA_LONG 0))))))))
 
 (defn render-into-realm!
   "realm.raytracing: copies the linear image into realm[0 .. 3*W*H) where the reference's loop

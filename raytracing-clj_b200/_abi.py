@@ -57,6 +57,9 @@ SYMBOLS = {
     "rtclj_render_multi": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Params),
                                      C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p,
                                      C.POINTER(Stats)]),
+    "rtclj_render_multi_ppm": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Params),
+                                         C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_size_t), C.POINTER(Stats)]),
     "rtclj_shard_plan": (C.c_int, [C.c_int32, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_size_t,
                                    C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)]),
     "rtclj_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),

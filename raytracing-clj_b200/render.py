@@ -96,6 +96,28 @@ def render(world, cam: Camera, samples_per_px: int = 100, max_depth: int = 50, *
     return out_linear, out_rgb8, st.as_dict()
 
 
+def render_ppm(world, cam: Camera, samples_per_px: int = 100, max_depth: int = 50, *, seed: int = 1,
+               flags: int = _abi.FLAGS_MAIN, samples_per_unit: int = 0, devices: Optional[Sequence[int]] = None):
+    """The render loop and the write-color! loop in one call (raytracing.clj:141-175): returns
+    (text of the P3 file as bytes, stats).  The image never visits the host: the shards are assembled on
+    devices[0] and the device P3 writer runs there (rtclj_render_multi_ppm)."""
+    lib = _abi.lib()
+    soa = _as_soa(world)
+    sc, cm = _scene_struct(soa), _camera_struct(cam)
+    prm = _abi.Params(int(samples_per_px), int(max_depth), int(seed), int(flags), int(samples_per_unit), 0, 0, 0, 0, 0)
+    devs = list(devices) if devices else [0]
+    arr = (C.c_int32 * len(devs))(*devs)
+    n = C.c_size_t()
+    _abi.check(lib.rtclj_render_multi_ppm(C.byref(sc), C.byref(cm), C.byref(prm), arr, len(devs), None, 0, C.byref(n), None))
+    store = bytearray(n.value)
+    buf = (C.c_char * n.value).from_buffer(store)
+    st = _abi.Stats()
+    _abi.check(lib.rtclj_render_multi_ppm(C.byref(sc), C.byref(cm), C.byref(prm), arr, len(devs), buf, n.value,
+                                          C.byref(n), C.byref(st)))
+    del buf
+    return bytes(memoryview(store)[: n.value]), st.as_dict()
+
+
 class Context:
     """Device-resident rendering: scene uploaded once, output left in device memory
     (pointers come from the caller, e.g. torch tensors), launches enqueued on the caller's

@@ -51,7 +51,7 @@ def test_bound_functions_exist_with_the_declared_arity():
     text = open(CLJ).read()
     hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rtclj_b200.h")).read(), flags=re.S)
     bound = re.findall(r'\(downcall "(\w+)"', text)
-    assert {"rtclj_render", "rtclj_render_multi", "rtclj_host_alloc", "rtclj_host_free", "rtclj_last_error",
+    assert {"rtclj_render", "rtclj_render_multi", "rtclj_render_multi_ppm", "rtclj_host_alloc", "rtclj_host_free", "rtclj_last_error",
             "rtclj_encode_ppm_p3_gpu"} <= set(bound)
     for sym in bound:
         decl = re.search(r"\b%s\s*\(([^)]*)\)\s*;" % sym, hdr)

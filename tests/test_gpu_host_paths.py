@@ -167,3 +167,30 @@ def test_strict_order_on_long_paths_goes_through_the_sample_buffer(extra):
             render.render(soa, cam, spp, 50, seed=seed, flags=flags | extra, samples_per_unit=spp, shard=(idx, 3, 2),
                           out_linear=lin, want_rgb8=False)
         assert np.array_equal(lin, lin_o)
+
+
+def test_render_to_ppm_text_equals_render_then_encode():
+    """rtclj_render_multi_ppm: render loop + write-color! loop (raytracing.clj:141-175) in one call, the shards
+    assembled on devices[0] by device-to-device copies and encoded there.  Same bytes as rendering to host
+    buffers and running the host P3 writer, for one GPU and for every GPU of the box, any tile height."""
+    n = device_count()
+    for world, cam, spp, depth, flags in ((S.main_hittables(), CAM.main_camera(200), 8, 50, _abi.FLAGS_MAIN),
+                                          (S.i_hittables(), CAM.i_camera(333), 4, 50, _abi.FLAGS_I),
+                                          (S.cover_hittables(7), CAM.main_camera(97, 55, **S.COVER_CAMERA), 6, 50, _abi.FLAGS_MAIN)):
+        _, rgb, st = render.render(world, cam, spp, depth, seed=3, flags=flags, want_linear=False)
+        want = render.encode_ppm(rgb)
+        for devs in ([0], list(range(n)), list(range(n))[::-1]):
+            text, st2 = render.render_ppm(world, cam, spp, depth, seed=3, flags=flags, devices=devs)
+            assert text == want, devs
+            assert st2["segments"] == st["segments"] and st2["n_devices"] == len(devs)
+    # sizing call and a buffer that is too small
+    lib = _abi.lib()
+    sc, cm = render._scene_struct(S.to_soa(S.main_hittables())), render._camera_struct(CAM.main_camera(64))
+    prm = _abi.Params(2, 5, 1, _abi.FLAGS_MAIN, 0, 0, 0, 0, 0, 0)
+    arr = (C.c_int32 * 1)(0)
+    ln = C.c_size_t()
+    assert lib.rtclj_render_multi_ppm(C.byref(sc), C.byref(cm), C.byref(prm), arr, 1, None, 0, C.byref(ln), None) == 0
+    assert ln.value >= 64 * 36 * 6
+    small = C.create_string_buffer(100)
+    assert lib.rtclj_render_multi_ppm(C.byref(sc), C.byref(cm), C.byref(prm), arr, 1, small, 100, C.byref(ln), None) == _abi.E_BUFFER
+    assert ln.value > 100 and b"capacity" in lib.rtclj_last_error()
