@@ -3,7 +3,9 @@ the rows its shard owns into ONE shared host framebuffer (/dev/shm), no data-pat
 rank 0 checks the assembled image against a single-process render.  The renderer here is the
 CPU oracle (this is a test: on the GPU box the same rows come from rtclj_render with shard_*);
 what is under test is the shard arithmetic, the disjoint-row gather and the reductions bench.py
-performs on its timings and segment counts."""
+performs on its timings and segment counts.  The library's own (C++) download plan for a shard is checked
+against the same arithmetic in tests/test_host.py::test_shard_plan_covers_exactly_the_shards_rows; the GPU
+side of N > 1 runs in tests/test_gpu_host_paths.py (one process, several devices) and in bench.py."""
 import os
 import sys
 
@@ -36,10 +38,17 @@ def _worker(rank, world, port, shm_path, result_path):
     fb = np.memmap(shm_path, dtype=np.float64, mode="r+", shape=(H, W, 3))
     mine = render.shard_rows(H, rank, world, 4)
     segs = 0
-    for j in mine:  # each rank writes only its own rows
+    local = np.zeros((H, W, 3), dtype=np.float64)   # this rank's "device image": full-size layout, own rows filled
+    for j in mine:
         lin, _, st = O.render(soa, cam, 6, 50, seed=3, flags=O.FLAGS_MAIN, rows=(j, j + 1), want_rgb8=False)
-        fb[j] = lin[j]
+        local[j] = lin[j]
         segs += st.segments
+    # the gather: the copies the LIBRARY plans for this shard (rtclj_shard_plan, the C++ behind rtclj_render's
+    # download), applied to the shared framebuffer -- each rank writes only its own rows
+    src, dst = local.reshape(-1).view(np.uint8), np.asarray(fb).reshape(-1).view(np.uint8)
+    for off, pitch, width, height in render.shard_plan(H, W * 24, rank, world, 4, 4096):
+        for r in range(height):
+            dst[off + r * pitch: off + r * pitch + width] = src[off + r * pitch: off + r * pitch + width]
     fb.flush()
     t = torch.tensor([float(segs)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)           # whole-job segment count
