@@ -181,11 +181,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="BASELINE.json config; c3 is the headline, the others are reported the same way")
-    ap.add_argument("--kernel", default=None, choices=["lane", "lane2", "wave"],
+    ap.add_argument("--kernel", default=None, choices=["lane", "lane2", "wave", "split"],
                     help="small-scene kernel to time (A/B); default: the library's choice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip strict_order / e2e_single_process")
     ap.add_argument("--spp", type=int, default=None, help="override the workload's spp (invalid as a bench value)")
+    ap.add_argument("--spu", type=int, default=0, help="samples per work unit for the timed steps (tuning; 0 = the library's choice)")
     args = ap.parse_args()
     wl = workloads()[args.workload]
     if args.spp:
@@ -223,7 +224,7 @@ def main():
     shard = (rank, world_size, SHARD_ROWS) if world_size > 1 else None
     flags = wl["flags"]
     if args.kernel:
-        flags |= {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL}[args.kernel]
+        flags |= {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL, "split": _abi.F_SPLIT_KERNEL}[args.kernel]
     lib = _abi.lib()
 
     # arithmetic peaks of this GPU (pure-FMA kernels), before the timed region
@@ -242,7 +243,7 @@ def main():
         def step():
             ctx.render(cam, spp, depth, seed=1, flags=flags, shard=shard, samples_per_unit=samples_per_unit,
                        d_out_linear=out_lin.data_ptr(), d_out_rgb8=out_rgb.data_ptr(), stream=stream)
-        for _ in range(max(3, args.warmup) if samples_per_unit == 0 else 1):
+        for _ in range(max(3, args.warmup) if samples_per_unit == args.spu else 1):
             step()
         barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
@@ -267,7 +268,7 @@ def main():
     barrier()
     if rank == 0:
         sampler.start()
-    total_ms, segs_per_step, kernel_ms, seg_local, spu_used = timed_device_steps(args.steps)
+    total_ms, segs_per_step, kernel_ms, seg_local, spu_used = timed_device_steps(args.steps, samples_per_unit=args.spu)
     clocks = sampler.stop() if rank == 0 else None
     value = segs_per_step * args.steps / (total_ms * 1e-3)
 

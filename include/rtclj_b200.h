@@ -79,12 +79,13 @@ enum {
   RTCLJ_F_QUANT_LINEAR = 32u,   /* 8-bit = int(255.999*c), no gamma, raytracing_i.clj:170   */
   RTCLJ_F_NO_CULL = 1u << 16,   /* debugging: skip the fp32 cull, test every sphere in fp64 */
   RTCLJ_F_SMEM_TABLE = 1u << 17, /* testing: use the shared-memory-table kernel even for a small scene */
-  /* Scenes of <= 512 spheres have three kernels that produce the same image; these select one
+  /* Scenes of <= 512 spheres have four kernels that produce the same image; these select one
    * explicitly (A/B timing, tests).  Without them the library uses the fastest one measured on the
    * bench workload. */
   RTCLJ_F_LANE_KERNEL = 1u << 18,  /* one path per lane (round 1)                                   */
   RTCLJ_F_WAVE_KERNEL = 1u << 19,  /* wavefront kernel: path state in shared memory, per-phase queues */
-  RTCLJ_F_LANE2_KERNEL = 1u << 20  /* two paths per lane, culled together                            */
+  RTCLJ_F_LANE2_KERNEL = 1u << 20, /* two paths per lane, culled together                            */
+  RTCLJ_F_SPLIT_KERNEL = 1u << 21  /* dedicated cull warps (four rays per lane) + path warps          */
 };
 #define RTCLJ_FLAGS_MAIN                                                               \
   (RTCLJ_F_NEAR_ZERO_GUARD | RTCLJ_F_SCHLICK | RTCLJ_F_REVERSE_PRODUCT | RTCLJ_F_MEAN_DIVIDE)

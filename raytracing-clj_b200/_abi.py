@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("RTCLJ_LIB") or os.path.join(HERE, "librtclj_b200.so")
 LAMBERTIAN, METAL, DIELECTRIC = 0, 1, 2
 F_NEAR_ZERO_GUARD, F_SCHLICK, F_REVERSE_PRODUCT, F_MEAN_DIVIDE = 1, 2, 4, 8
 F_NORMAL_SHADING, F_QUANT_LINEAR, F_NO_CULL, F_SMEM_TABLE = 16, 32, 1 << 16, 1 << 17
-F_LANE_KERNEL, F_WAVE_KERNEL, F_LANE2_KERNEL = 1 << 18, 1 << 19, 1 << 20
+F_LANE_KERNEL, F_WAVE_KERNEL, F_LANE2_KERNEL, F_SPLIT_KERNEL = 1 << 18, 1 << 19, 1 << 20, 1 << 21
 FLAGS_MAIN = F_NEAR_ZERO_GUARD | F_SCHLICK | F_REVERSE_PRODUCT | F_MEAN_DIVIDE
 FLAGS_REALM = 0
 FLAGS_I = F_NORMAL_SHADING | F_QUANT_LINEAR

@@ -5,6 +5,7 @@
 #include "rtclj_kernels.cuh"
 #include "rtclj_wave_kernel.cuh"
 #include "rtclj_lane2_kernel.cuh"
+#include "rtclj_split_kernel.cuh"
 #include "rtclj_p3_kernels.cuh"
 #include "rtclj_error.h"
 
@@ -244,6 +245,8 @@ int rtclj_ctx_create(int32_t device, rtclj_ctx** out) {
   CU(cudaFuncSetAttribute(render_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WaveSmem::total));
   CU(cudaFuncSetAttribute(render_lane2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lane2Smem::total));
   CU(cudaFuncSetAttribute(render_lane2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lane2Smem::total));
+  CU(cudaFuncSetAttribute(render_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitSmem::total));
+  CU(cudaFuncSetAttribute(render_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitSmem::total));
   *out = guard.release();
   return RTCLJ_OK;
 }
@@ -380,7 +383,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   const bool want_out = d_out_linear || d_out_rgb8;
   // scenes of <= 512 spheres: three kernels produce the same image (tests); the default is the fastest
   // measured on the bench workload, the flags select the others for A/B timing
-  enum { SMALL_LANE1, SMALL_LANE2, SMALL_WAVE };
+  enum { SMALL_LANE1, SMALL_LANE2, SMALL_WAVE, SMALL_SPLIT };
   // Two paths per lane pay when the cull dominates (many spheres) and the render is long enough to hide
   // the longer tail of twice as many work units in flight: measured on a B200 (profiles/r2_kernel_ab.md),
   // cover scene 1920x1080: 500 spp 543.7 vs 561.6 ms, 16 spp 19.6 vs 18.6 ms; 5 spheres: 11.7 vs 11.0 ms.
@@ -392,8 +395,10 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   if (prm->flags & RTCLJ_F_LANE_KERNEL) small = SMALL_LANE1;
   if (prm->flags & RTCLJ_F_LANE2_KERNEL) small = SMALL_LANE2;
   if (prm->flags & RTCLJ_F_WAVE_KERNEL) small = SMALL_WAVE;
+  if (prm->flags & RTCLJ_F_SPLIT_KERNEL) small = SMALL_SPLIT;
   const bool wave = run_kernel && const_tab && small == SMALL_WAVE;    // also finishes the pixels itself
   const bool lane2 = run_kernel && const_tab && small == SMALL_LANE2;
+  const bool split = run_kernel && const_tab && small == SMALL_SPLIT;
 
   // Summation unit.  Primary-ray renders (max-depth 1, normal shading) are bit-exact contracts and short
   // paths: they default to the reference's strict sequential sum (raytracing.clj:142-155,
@@ -472,6 +477,14 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
         P.arrive = c->arrive.p;
       }
       render_wave_kernel<<<grid, kWT, WaveSmem::total, stream>>>(P);
+    } else if (split) {
+      P.stack_stride = (unsigned)grid * (unsigned)kSplitW * 2u;
+      if (prm->max_depth > 1) {
+        CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
+        P.stack = c->stack.p;
+      }
+      if (sample_buf) render_split_kernel<true><<<grid, kSplitThreads, SplitSmem::total, stream>>>(P);
+      else render_split_kernel<false><<<grid, kSplitThreads, SplitSmem::total, stream>>>(P);
     } else if (lane2) {
       P.stack_stride = (unsigned)grid * (unsigned)kT2 * 2u;
       if (prm->max_depth > 1) {

@@ -63,13 +63,14 @@ def test_device_list_is_validated():
         assert e.value.code == _abi.E_INVALID and str(e.value)
 
 
-@pytest.mark.parametrize("which", ["lane", "lane2", "wave"])
+@pytest.mark.parametrize("which", ["lane", "lane2", "wave", "split"])
 def test_two_scenes_render_concurrently_on_one_device(which):
     """Two contexts, two streams, two different small scenes, launches interleaved without any
     synchronisation between them.  The cull table travels with each launch (kernel parameters); with
     round 1's module-global __constant__ table the second upload corrupted the first render."""
     import torch
-    extra = {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL}[which]
+    extra = {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL,
+             "split": _abi.F_SPLIT_KERNEL}[which]
     jobs = [(S.cover_hittables(7), CAM.main_camera(256, 144, **S.COVER_CAMERA), _abi.FLAGS_MAIN, 3),
             (S.realm_hittables(), CAM.realm_camera(256), _abi.FLAGS_REALM, 4)]
     want = [render.render(w, cam, 24, 50, seed=seed, flags=fl | extra, samples_per_unit=8) for w, cam, fl, seed in jobs]
@@ -148,7 +149,8 @@ def test_pinned_caller_buffers_are_written_directly_and_equal_pageable_ones():
         _abi.check(lib.rtclj_host_unregister(C.c_void_p(buf.ctypes.data)))
 
 
-@pytest.mark.parametrize("extra", [_abi.F_LANE_KERNEL, _abi.F_LANE2_KERNEL, _abi.F_SMEM_TABLE, _abi.F_WAVE_KERNEL])
+@pytest.mark.parametrize("extra", [_abi.F_LANE_KERNEL, _abi.F_LANE2_KERNEL, _abi.F_SMEM_TABLE, _abi.F_WAVE_KERNEL,
+                                   _abi.F_SPLIT_KERNEL])
 def test_strict_order_on_long_paths_goes_through_the_sample_buffer(extra):
     """samples_per_unit >= spp on a full-depth render of >= 64 spp: the samples are traced in small units,
     every sample's colour is stored and finalize_kernel adds them in sample order -- bit for bit the

@@ -156,7 +156,8 @@ def test_both_kernels_agree_with_the_oracle():
             assert st_g["segments"] == st_o.segments
 
 
-SMALL_KERNELS = {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL}
+SMALL_KERNELS = {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL,
+                 "split": _abi.F_SPLIT_KERNEL}
 
 
 @pytest.mark.parametrize("which", sorted(SMALL_KERNELS))

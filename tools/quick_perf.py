@@ -21,7 +21,7 @@ def peaks():
 def run(name, world, cam, spp, depth, flags, reps=3, **kw):
     which = os.environ.get("RTCLJ_QP_KERNEL")
     if which:
-        flags |= {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL}[which]
+        flags |= {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL, "split": _abi.F_SPLIT_KERNEL}[which]
         name += f"[{which}]"
     if os.environ.get("RTCLJ_QP_STRICT"):
         kw["samples_per_unit"] = spp
