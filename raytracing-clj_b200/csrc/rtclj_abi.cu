@@ -386,9 +386,10 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   enum { SMALL_LANE1, SMALL_LANE2, SMALL_WAVE, SMALL_SPLIT };
   // Two paths per lane pay when the cull dominates (many spheres) and the render is long enough to hide
   // the longer tail of twice as many work units in flight: measured on a B200 (profiles/r2_kernel_ab.md),
-  // cover scene 1920x1080: 500 spp 543.7 vs 561.6 ms, 16 spp 19.6 vs 18.6 ms; 5 spheres: 11.7 vs 11.0 ms.
+  // cover scene 1920x1080: 500 spp 543.7 vs 561.6 ms, one eighth of it (an 8-GPU shard, 1.3e8 samples) 70.85 vs
+  // 71.40 ms, 16 spp (3.3e7 samples) 19.6 vs 18.6 ms; 5 spheres: 11.7 vs 11.0 ms.  Break-even near 9e7 samples.
   const double total_samples = (double)local_pixels * (double)prm->spp;
-  int small = (c->n >= 64 && total_samples >= 134217728.0) ? SMALL_LANE2 : SMALL_LANE1;
+  int small = (c->n >= 64 && total_samples >= 1.0e8) ? SMALL_LANE2 : SMALL_LANE1;
 #ifdef RTCLJ_DEFAULT_SMALL_KERNEL
   small = RTCLJ_DEFAULT_SMALL_KERNEL;
 #endif
