@@ -381,7 +381,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   const bool run_kernel = prm->max_depth > 0;
   const bool const_tab = use_const_table(c->nhalf) && !(prm->flags & RTCLJ_F_SMEM_TABLE);
   const bool want_out = d_out_linear || d_out_rgb8;
-  // scenes of <= 512 spheres: three kernels produce the same image (tests); the default is the fastest
+  // scenes of <= 512 spheres: four kernels produce the same image (tests); the default is the fastest
   // measured on the bench workload, the flags select the others for A/B timing
   enum { SMALL_LANE1, SMALL_LANE2, SMALL_WAVE, SMALL_SPLIT };
   // Two paths per lane pay when the cull dominates (many spheres) and the render is long enough to hide

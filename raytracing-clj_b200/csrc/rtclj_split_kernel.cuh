@@ -7,7 +7,7 @@
 // is 64 % busy and the issue slots 76 %: the warps of a sub-partition drift into the same phase -- all shading
 // (the pipe idles) or several culling (they fight for it).  A dedicated cull warp should feed the pipe evenly.
 //
-// MEASURED (DESIGN.md section 4.4): bit-exact, and SLOWER -- 639 ms per bench frame against 544 ms for
+// MEASURED (DESIGN.md section 4.3b): bit-exact, and SLOWER -- 639 ms per bench frame against 544 ms for
 // render_lane2_kernel (FMA pipe 56 % busy, issue slots 72 %).  Sixteen path warps do not hide the latency of
 // the fp64 resolve / shade chains; the four warps given to the cull are missed there.  Kept behind
 // RTCLJ_F_SPLIT_KERNEL as the measured answer to "why not warp-specialise".

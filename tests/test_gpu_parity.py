@@ -162,7 +162,7 @@ SMALL_KERNELS = {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave
 
 @pytest.mark.parametrize("which", sorted(SMALL_KERNELS))
 def test_every_small_scene_kernel_agrees_with_the_oracle(which):
-    """Scenes of <= 512 spheres have three kernels (one path per lane, two paths per lane, wavefront);
+    """Scenes of <= 512 spheres have four kernels (one path per lane, two paths per lane, wavefront, dedicated cull warps);
     the library picks one, the RTCLJ_F_*_KERNEL flags select each.  All of them against the oracle:
     every variant, defocus, glass, depth caps (attenuation stack, K_END), chunked units, ragged sizes,
     exact ties, an empty list, shards, and the device-resident call."""
