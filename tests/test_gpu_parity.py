@@ -132,7 +132,10 @@ def test_cull_fuzz_against_exhaustive_scan():
                               look_at=tuple(float(x) for x in pick), defocus_angle=float(rng.choice([0.0, 2.0])),
                               focus_dist=float(np.linalg.norm(look_from - pick) + 1e-9 * scale))
         variant = O.FLAGS_REALM if case % 2 else O.FLAGS_MAIN   # forward / innermost-first product, Schlick on / off
-        for extra in (0, _abi.F_SMEM_TABLE):
+        # every kernel takes its turn: the library's choice and the shared-memory-table kernel always, plus one of
+        # the other small-scene kernels (two paths per lane, wavefront, dedicated cull warps)
+        rotating = (_abi.F_LANE2_KERNEL, _abi.F_WAVE_KERNEL, _abi.F_SPLIT_KERNEL)[case % 3]
+        for extra in (0, _abi.F_SMEM_TABLE) + ((rotating,) if n <= 512 else ()):
             a, ra, sa = gpu(world, cam, 4, 12, seed=case, flags=variant | extra, samples_per_unit=4)
             b, rb, sb = gpu(world, cam, 4, 12, seed=case, flags=variant | extra | _abi.F_NO_CULL, samples_per_unit=4)
             assert sa["segments"] == sb["segments"] and np.array_equal(a, b, equal_nan=True), (case, extra, n, scale)
