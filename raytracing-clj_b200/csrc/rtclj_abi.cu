@@ -68,6 +68,7 @@ struct rtclj_ctx {
   int n = 0, nhalf = 0;  // spheres; 16-sphere half blocks of the padded cull table
   double shift[3] = {0, 0, 0};
   DevBuf<float4> geom32;
+  DevBuf<float4> geomA;                 // one {cx, cy, cz, Ws} per sphere: what the fp32 prefilter loads
   DevBuf<Geom64> geom64;
   DevBuf<MatRec> mat;
   DevBuf<double> partial;
@@ -255,7 +256,7 @@ void rtclj_ctx_destroy(rtclj_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-  c->geom32.release(); c->geom64.release(); c->mat.release(); c->partial.release();
+  c->geom32.release(); c->geomA.release(); c->geom64.release(); c->mat.release(); c->partial.release();
   c->counters.release(); c->stack.release(); c->arrive.release(); c->sample_buf.release(); c->out_linear.release(); c->out_rgb8.release();
   c->p3_state.release(); c->p3_in.release(); c->p3_text.release();
   for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->p3_ev0, c->p3_ev1, c->pin_ev[0], c->pin_ev[1]})
@@ -307,6 +308,7 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
   std::vector<Geom64> g64((size_t)std::max(n, 1));
   std::vector<MatRec> mats((size_t)std::max(n, 1));
   std::vector<float> g32((size_t)std::max(npad, 2) * 4);
+  std::vector<float4> gA((size_t)std::max(n, 1));
   for (int i = 0; i < npad; ++i) {
     float cx = 0.f, cy = 0.f, cz = 0.f, r2s = -1e30f;  // padding never survives the cull
     if (i < n) {
@@ -345,14 +347,17 @@ int rtclj_ctx_set_scene(rtclj_ctx* c, const rtclj_scene* s) {
     const int p = i >> 1, h = i & 1;
     float* v = g32.data() + (size_t)p * 8;
     v[0 + h] = cx; v[2 + h] = cy; v[4 + h] = cz; v[6 + h] = r2s;
+    if (i < n) gA[(size_t)i] = make_float4(cx, cy, cz, r2s);
   }
   CU(c->geom64.reserve((size_t)std::max(n, 1)));
   CU(c->mat.reserve((size_t)std::max(n, 1)));
   CU(c->geom32.reserve((size_t)std::max(npad, 2)));
+  CU(c->geomA.reserve((size_t)std::max(n, 1)));
   if (n > 0) {
     CU(cudaMemcpy(c->geom64.p, g64.data(), sizeof(Geom64) * (size_t)n, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->mat.p, mats.data(), sizeof(MatRec) * (size_t)n, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->geom32.p, g32.data(), sizeof(float) * 4 * (size_t)npad, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->geomA.p, gA.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice));
   }
   c->n = n; c->nhalf = nhalf;
   c->ctab_host.clear();
@@ -460,7 +465,7 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
     P.geom_bytes = (unsigned)std::min((size_t)c->nhalf * 256, (size_t)P.smem_blocks * 512);  // staged part
     P.shard_index = shard_index; P.shard_count = shard_count; P.shard_rows = shard_rows;
     P.nchunks = nchunks; P.spu = spu; P.total_units = total_units;
-    P.geom32 = c->geom32.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
+    P.geom32 = c->geom32.p; P.geomA = c->geomA.p; P.geom64 = c->geom64.p; P.mat = c->mat.p;
     P.partial = c->partial.p; P.queue = c->counters.p; P.stats = c->counters.p + 1;
     P.sample_buf = sample_buf; P.sample_stride = local_pixels;
     if (const_tab && !c->ctab_host.empty())

@@ -139,4 +139,9 @@ __global__ void __launch_bounds__(kT2, 1) render_lane2_kernel(const __grid_const
   }
 }
 
+// (The same loop with ONE path per lane built on path_step() was measured against render_kernel<true>: equal on
+// the cover scene, 6 % slower on realm's forward product -- formed from the stack instead of a running product
+// in registers -- and on primary-ray renders, which pay path_step's pixel / W division per sample.  So short
+// renders and tiny scenes stay on render_kernel<true>.)
+
 }  // namespace rtclj

@@ -316,14 +316,15 @@ __global__ void __launch_bounds__(kWT, 1) render_wave_kernel(const __grid_consta
               const int j = (__ffs(any) - 1) - nb_shift;
               any &= any - 1;
               cur = (unsigned)(unsigned short)~my_mask[j * kWT];
+              n_pref += (unsigned)__popc(cur);
               bbase = j * 16 - 16;  // __clz counts the 16 leading zeros too
             }
             const int bit = __clz(cur);
             cur &= ~(0x80000000u >> bit);
             int i = bbase + bit;
             if (i >= P.n) continue;
-            const float* gp = reinterpret_cast<const float*>(P.geom32) + (size_t)(i >> 1) * 8 + (i & 1);
-            const float cx = __ldg(gp), cy = __ldg(gp + 2), cz = __ldg(gp + 4), ws = __ldg(gp + 6);
+            const float4 g4 = __ldg(P.geomA + i);
+            const float cx = g4.x, cy = g4.y, cz = g4.z, ws = g4.w;
             const float bb = fmaf(cz, dhz, fmaf(cy, dhy, fmaf(cx, dhx, nbetaf)));
             const float ss = fmaf(cz, 2.0f * ofz, fmaf(cy, 2.0f * ofy, fmaf(cx, 2.0f * ofx, ws + kqf)));
             const float dd = fmaf(bb, bb, ss);                           // >= D_true (inflated)
@@ -332,7 +333,6 @@ __global__ void __launch_bounds__(kWT, 1) render_wave_kernel(const __grid_consta
             const float far_hi = bb + sq + eb;
             float lo = bb - sq - eb;                                     // <= every root of sphere i
             const float clo_hi = __double2float_ru(closest) * len32 * (1.0f + 16.0f * kEps32);
-            n_pref++;
             if (far_hi < tmin_lo || lo > clo_hi) continue;
             // keep the three candidates with the smallest lower bounds, sorted; a fourth is tested on the spot
             if (lo < lo1) { const int ti = c1; const float tl = lo1; c1 = i; lo1 = lo; i = ti; lo = tl; }
