@@ -7,7 +7,7 @@
 // is 64 % busy and the issue slots 76 %: the warps of a sub-partition drift into the same phase -- all shading
 // (the pipe idles) or several culling (they fight for it).  A dedicated cull warp should feed the pipe evenly.
 //
-// MEASURED: bit-exact, and SLOWER -- 639 ms per bench frame against 544 ms for
+// MEASURED: bit-exact, and SLOWER -- 627 ms per bench frame against 536 ms for
 // render_lane2_kernel (FMA pipe 56 % busy, issue slots 72 %).  Sixteen path warps do not hide the latency of
 // the fp64 resolve / shade chains; the four warps given to the cull are missed there.  Kept behind
 // RTCLJ_F_SPLIT_KERNEL as the measured answer to "why not warp-specialise".
@@ -61,12 +61,14 @@ __global__ void __launch_bounds__(kSplitThreads, 1) render_split_kernel(const __
       int pair_flag = 0;
       if (lane < 8) { pair_flag = 2 * (warp + kSplitCullWarps * (lane >> 1)) + (lane & 1); st = state[pair_flag]; }
       const unsigned ready = __ballot_sync(FULL, st == SS_SUBMITTED) & 0xffu;
-      const unsigned alive = __ballot_sync(FULL, st != SS_DEAD) & 0xffu;
-      if (alive == 0u) break;
-      // Take whatever is there (up to four sets).  Passes then run ~56 % full, but waiting for full ones
-      // (unless a path warp had both its sets here) was measured and is worse -- 808 instead of 639 ms per
-      // bench frame: the path warps, not this warp, are the bottleneck.
-      if (ready == 0u) {
+      // (ptxas keeps the cull's table loads uniform only with the loop exit nested in this ONE branch: a second
+      // `continue`, or the exit test at the top of the loop, silently turns them into per-lane LDC -- 798 instead
+      // of 627 ms per bench frame; tests/test_build_artifacts.py checks the SASS)
+      // whatever is there, up to four sets (waiting for FULL passes -- unless a path warp has both its sets here --
+      // was measured too: 627.8 against 627.4 ms per bench frame, no difference)
+      const bool go = ready != 0u;
+      if (!go) {
+        if (__all_sync(FULL, st == SS_DEAD)) break;
         __nanosleep(32);
         continue;
       }

@@ -39,7 +39,7 @@ def test_only_sm_100a_code_is_shipped():
     assert archs == {"sm_100a"}, archs
 
 
-@pytest.mark.parametrize("key", ["render_wave_kernel", "render_kernelILb1", "render_lane2_kernel"])
+@pytest.mark.parametrize("key", ["render_wave_kernel", "render_kernelILb1", "render_lane2_kernel", "render_split_kernel"])
 def test_small_scene_cull_takes_its_table_through_uniform_registers(sass, key):
     """<= 512 spheres: the cull table is a kernel parameter and must reach FFMA2 as UNIFORM operands
     (LDCU.64 UR, c[0x0][UR+..] -> FFMA2 R, R.F32, UR.F32x2, ..).  ptxas silently falls back to per-lane LDC
