@@ -114,7 +114,7 @@ __device__ __forceinline__ void path_step(const KParams& P, PathRegs& pr, PathCo
         const float lo_i = s2 == 0 ? lo1 : (s2 == 1 ? lo2 : lo3);
         if (ci < 0) break;
         if (s2 && !(lo_i <= __double2float_ru(closest) * vw.len32 * (1.0f + 16.0f * kEps32))) break;
-        exact_test_lex(P.geom64, ci, O, D, a, ya, a_ok, closest, best);
+        exact_test_lex(P.geom64, ci, O, D, a, ya, a_ok, closest, best);  // (out of line it costs 2.8 % of a bench frame)
         n_exact++;
       }
     }
