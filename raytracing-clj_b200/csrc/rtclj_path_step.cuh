@@ -157,9 +157,9 @@ __device__ __forceinline__ void path_step(const KParams& P, PathRegs& pr, PathCo
 #pragma unroll 1
         for (;;) {
           const unsigned wa = half ? w.z : w.x, wb = half ? w.w : w.y;
-          cx = sym((double)(wa & 0x1fffffu) * (1.0 / 2097152.0));
-          cy = sym((double)((wa >> 21) | ((wb & 0x3ffu) << 11)) * (1.0 / 2097152.0));
-          cz = sym((double)((wb >> 10) & 0x1fffffu) * (1.0 / 2097152.0));
+          cx = sym21(wa & 0x1fffffu);
+          cy = sym21((wa >> 21) | ((wb & 0x3ffu) << 11));
+          cz = sym21((wb >> 10) & 0x1fffffu);
           l2 = cx * cx + cy * cy + cz * cz;
           if ((l2 > 1e-160 && l2 <= 1.0) || block == 0xffffffu) break;
           if (half == 0) { half = 1; continue; }
@@ -293,13 +293,13 @@ __device__ __forceinline__ void path_step(const KParams& P, PathRegs& pr, PathCo
     const d3 ps = add(add(ld3(P.p00), muls(ld3(P.du), sx)), muls(ld3(P.dv), sy));
     O = ld3(P.center);
     if (P.use_defocus) {  // vec3a/random-in-unit-disk, vec3a.clj:81-86
-      double px = sym(u24(w.z)), py = sym(u24(w.w));
+      double px = sym24(w.z), py = sym24(w.w);
       unsigned block = 0;
       int half = 1;
       while (!(px * px + py * py < 1.0) && block < 0xffffffu) {
         if (half == 1) { w = philox_ni(pixel, (unsigned)k, 0u, ++block, P.k0, P.k1); half = 0; } else half = 1;
-        px = sym(u24(half ? w.z : w.x));
-        py = sym(u24(half ? w.w : w.y));
+        px = sym24(half ? w.z : w.x);
+        py = sym24(half ? w.w : w.y);
       }
       O = add(add(O, muls(ld3(P.ddu), px)), muls(ld3(P.ddv), py));  // raytracing.clj:89-93
     }
