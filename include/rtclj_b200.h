@@ -77,7 +77,9 @@ enum {
                                    off = sum * (1/spp), realm/raytracing.clj:25,344         */
   RTCLJ_F_NORMAL_SHADING = 16u, /* hit -> 0.5*(N+1), no bounces, raytracing_i.clj:59-73     */
   RTCLJ_F_QUANT_LINEAR = 32u,   /* 8-bit = int(255.999*c), no gamma, raytracing_i.clj:170   */
-  RTCLJ_F_NO_CULL = 1u << 16,   /* debugging: skip the fp32 cull, test every sphere in fp64 */
+  RTCLJ_F_NO_CULL = 1u << 16,   /* skip the fp32 cull, test every sphere in fp64 (same image; the library
+                                   chooses this by itself for scenes of <= 2 spheres, <= 6 when only primary
+                                   rays are traced, where it is faster) */
   RTCLJ_F_SMEM_TABLE = 1u << 17, /* testing: use the shared-memory-table kernel even for a small scene */
   /* Scenes of <= 512 spheres have four kernels that produce the same image; these select one
    * explicitly (A/B timing, tests).  Without them the library uses the fastest one measured on the

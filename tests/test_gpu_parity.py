@@ -101,6 +101,20 @@ def test_cull_equals_exhaustive_fp64_scan():
     assert sb["exact_tests"] == sb["segments"] * len(world)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 6, 7])
+def test_handful_of_spheres_scans_exhaustively_and_stays_bit_exact(n):
+    """Scenes of one or two spheres (six for primary-ray renders) skip the fp32 cull: rtclj_ctx_render picks the
+    exhaustive fp64 scan by itself (faster there, rtclj_abi.cu).  Same image either way, and equal to the oracle."""
+    world = (S.main_hittables() + S.cover_hittables(7)[4:8])[:n]
+    for flags, cam, scans in ((O.FLAGS_MAIN, CAM.main_camera(160), n <= 2), (O.FLAGS_I, CAM.i_camera(160), n <= 6)):
+        st = assert_same(world, cam, 12, 50, 5, flags)
+        assert (st["exact_tests"] == st["segments"] * n) == scans, (n, flags, st)
+        lin_c, rgb_c, st_c = gpu(world, cam, 12, 50, seed=5, flags=flags | _abi.F_LANE2_KERNEL, samples_per_unit=12)  # culls
+        lin_d, rgb_d, st_d = gpu(world, cam, 12, 50, seed=5, flags=flags, samples_per_unit=12)
+        assert np.array_equal(lin_c, lin_d) and np.array_equal(rgb_c, rgb_d) and st_c["segments"] == st_d["segments"]
+        assert st_c["exact_tests"] < st_c["segments"] * n or n == 1
+
+
 def test_cull_fuzz_against_exhaustive_scan():
     """The conservative fp32 cull + prefilter against the exhaustive fp64 scan on random scenes at
     scales from 1e-3 to 1e9, cameras inside, near and far, grazing rays, tiny and huge radii, clustered

@@ -23,6 +23,9 @@ def run(name, world, cam, spp, depth, flags, reps=3, **kw):
     if which:
         flags |= {"lane": _abi.F_LANE_KERNEL, "lane2": _abi.F_LANE2_KERNEL, "wave": _abi.F_WAVE_KERNEL, "split": _abi.F_SPLIT_KERNEL}[which]
         name += f"[{which}]"
+    if os.environ.get("RTCLJ_QP_FLAGS"):
+        flags |= int(os.environ["RTCLJ_QP_FLAGS"], 0)
+        name += f"[+{os.environ['RTCLJ_QP_FLAGS']}]"
     if os.environ.get("RTCLJ_QP_STRICT"):
         kw["samples_per_unit"] = spp
         name += "[strict]"
