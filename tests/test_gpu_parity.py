@@ -115,6 +115,27 @@ def test_handful_of_spheres_scans_exhaustively_and_stays_bit_exact(n):
         assert st_c["exact_tests"] < st_c["segments"] * n or n == 1
 
 
+@pytest.mark.parametrize("n", [0, 1, 2, 5, 6])
+def test_primary_ray_kernel_equals_the_general_kernel_and_the_oracle(n):
+    """Primary rays only (normal shading, or max-depth 1) on <= 6 spheres run render_primary_kernel; RTCLJ_F_LANE_KERNEL
+    keeps render_kernel.  Same linear image, 8-bit image and counters: whole pixels (strict), chunks, a shard, with
+    and without the defocus disk, both quantisations -- and equal to the oracle."""
+    world = (S.main_hittables() + S.cover_hittables(7)[4:8])[:n]
+    cases = (("normal", O.FLAGS_I, CAM.i_camera(160), 50), ("normal-depth1", O.FLAGS_I, CAM.i_camera(96), 1),
+             ("main-depth1-defocus", O.FLAGS_MAIN, CAM.main_camera(160), 1), ("realm-depth1", O.FLAGS_REALM, CAM.i_camera(160), 1))
+    for name, flags, cam, depth in cases:
+        for unit in (0, 5):
+            st = assert_same(world, cam, 12, depth, 11, flags, unit=unit)
+            assert st["exact_tests"] == st["segments"] * n and st["segments"] == st["samples"], (name, st)
+            a = gpu(world, cam, 12, depth, seed=11, flags=flags, samples_per_unit=unit if unit else 12)
+            b = gpu(world, cam, 12, depth, seed=11, flags=flags | _abi.F_LANE_KERNEL, samples_per_unit=unit if unit else 12)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2]["segments"] == b[2]["segments"], (name, unit)
+        a = gpu(world, cam, 9, depth, seed=4, flags=flags, shard=(1, 3, 2))
+        b = gpu(world, cam, 9, depth, seed=4, flags=flags | _abi.F_LANE_KERNEL, shard=(1, 3, 2))
+        rows = render.shard_rows(cam.height, 1, 3, 2)
+        assert np.array_equal(a[0][rows], b[0][rows]) and np.array_equal(a[1][rows], b[1][rows]) and a[2]["samples"] == b[2]["samples"], name
+
+
 def test_cull_fuzz_against_exhaustive_scan():
     """The conservative fp32 cull + prefilter against the exhaustive fp64 scan on random scenes at
     scales from 1e-3 to 1e9, cameras inside, near and far, grazing rays, tiny and huge radii, clustered
