@@ -17,9 +17,18 @@
 namespace rtclj {
 
 constexpr int kPrimarySpheres = 6;    // the measured crossover of scan vs cull for primary rays (rtclj_abi.cu)
-constexpr int kPrimaryThreads = 256;
+#ifndef RTCLJ_PRIM_THREADS
+#define RTCLJ_PRIM_THREADS 256
+#endif
+#ifndef RTCLJ_PRIM_MINB
+#define RTCLJ_PRIM_MINB 4
+#endif
+#ifndef RTCLJ_PRIM_UNROLL
+#define RTCLJ_PRIM_UNROLL 1
+#endif
+constexpr int kPrimaryThreads = RTCLJ_PRIM_THREADS;
 
-__global__ void __launch_bounds__(kPrimaryThreads, 4) render_primary_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(kPrimaryThreads, RTCLJ_PRIM_MINB) render_primary_kernel(const __grid_constant__ KParams P) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const bool normal_shading = (P.flags & F_NORMAL_SHADING) != 0;
@@ -75,8 +84,14 @@ __global__ void __launch_bounds__(kPrimaryThreads, 4) render_primary_kernel(cons
       const bool a_ok = recip_safe(a);
       int best = -1;
       double closest = __longlong_as_double(0x7ff0000000000000LL);
+#if RTCLJ_PRIM_UNROLL
+#pragma unroll
+      for (int i = 0; i < kPrimarySpheres; ++i) {
+        if (i >= n) break;
+#else
 #pragma unroll 1
       for (int i = 0; i < n; ++i) {
+#endif
         const double gr = G[4 * i + 3];
         const d3 oc = mk(G[4 * i] - O.x, G[4 * i + 1] - O.y, G[4 * i + 2] - O.z);
         const double h = dot(D, oc);
