@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -517,8 +518,22 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
         CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
         P.stack = c->stack.p;
       }
+#ifdef RTCLJ_TAIL_PROBE
+      const size_t probe_words = (size_t)grid * (kT2 / 32) * 4 * 2;
+      CU(c->arrive.reserve(probe_words));
+      CU(cudaMemsetAsync(c->arrive.p, 0, probe_words * sizeof(unsigned), stream));
+      P.arrive = c->arrive.p;
+#endif
       if (sample_buf) render_lane2_kernel<true><<<grid, kT2, Lane2Smem::total, stream>>>(P);
       else render_lane2_kernel<false><<<grid, kT2, Lane2Smem::total, stream>>>(P);
+#ifdef RTCLJ_TAIL_PROBE
+      if (const char* path = std::getenv("RTCLJ_TAIL_PROBE_FILE")) {
+        std::vector<unsigned> host(probe_words);
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaMemcpy(host.data(), c->arrive.p, probe_words * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (FILE* f = std::fopen(path, "wb")) { std::fwrite(host.data(), sizeof(unsigned), probe_words, f); std::fclose(f); }
+      }
+#endif
     } else {
       P.stack_stride = (unsigned)grid * (unsigned)threads_of(const_tab);
       if (prm->flags & RTCLJ_F_REVERSE_PRODUCT) {

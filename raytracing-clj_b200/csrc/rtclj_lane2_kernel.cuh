@@ -55,7 +55,19 @@ __global__ void __launch_bounds__(kT2, 1) render_lane2_kernel(const __grid_const
   // the waiting path starts FRESH as well
   wU[6 * kT2] = (unsigned)PS_FRESH;
 
+#ifdef RTCLJ_TAIL_PROBE  // tuning builds only (tools/tail_probe.py): when does each warp start, first run dry, end?
+  unsigned long long t_start, t_dry = 0, t_end;
+  unsigned n_iter = 0, n_iter_dry = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
   for (;;) {
+#ifdef RTCLJ_TAIL_PROBE
+    n_iter++;
+    if (t_dry == 0 && __any_sync(FULL, status == PS_DEAD || wU[6 * kT2] == (unsigned)PS_DEAD)) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dry));
+      n_iter_dry = n_iter;
+    }
+#endif
     // ================================================================ (A) cull, both paths at once
     unsigned bany0 = 0, bany1 = 0;  // which blocks have a survivor (block j at bit 32 - nconst + j)
     {
@@ -128,6 +140,13 @@ __global__ void __launch_bounds__(kT2, 1) render_lane2_kernel(const __grid_const
     if (!__any_sync(FULL, status != PS_DEAD || wU[6 * kT2] != (unsigned)PS_DEAD)) break;
   }
 
+#ifdef RTCLJ_TAIL_PROBE
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+  if (lane == 0 && P.arrive) {
+    unsigned long long* rec = reinterpret_cast<unsigned long long*>(P.arrive) + ((size_t)blockIdx.x * (kT2 / 32) + (tid >> 5)) * 4;
+    rec[0] = t_start; rec[1] = t_dry; rec[2] = t_end; rec[3] = ((unsigned long long)n_iter << 32) | n_iter_dry;
+  }
+#endif
   // ---- counters: REDUX on 16-bit halves (each lane's count fits 32 bits), one atomic per warp
   {
     const unsigned v[5] = {pc.samples, pc.seg, pc.exact, 0u, pc.pref};

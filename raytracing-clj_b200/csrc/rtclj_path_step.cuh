@@ -265,8 +265,7 @@ __device__ __forceinline__ void path_step(const KParams& P, PathRegs& pr, PathCo
         if (ticket >= P.total_units) {
           status = PS_DEAD;
         } else {
-          unit = (unsigned)ticket;
-          const unsigned p_local = unit / (unsigned)P.nchunks;
+          const unsigned p_local = unit_of_ticket(P, (unsigned)ticket, unit);
           const int chunk = (int)(unit - p_local * (unsigned)P.nchunks);
           const int lr = (int)(p_local / (unsigned)P.W);
           const int pi = (int)(p_local - (unsigned)lr * (unsigned)P.W);

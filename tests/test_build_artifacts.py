@@ -79,3 +79,15 @@ def test_lane_kernels_fit_the_instruction_cache(sass):
         body = kernels(sass, key)[0]
         assert len(body) * 16 <= 34 * 1024, (key, len(body) * 16)
 
+
+
+def test_primary_ray_kernel_reads_no_memory_in_its_loop(sass):
+    """render_primary_kernel: the sphere constants come from the kernel parameters, the sums
+    live in registers -- no global / shared / local loads anywhere, no spills, and a body that fits the
+    instruction cache."""
+    body = kernels(sass, "render_primary_kernel")[0]
+    text = "\n".join(body)
+    assert not re.search(r"\b(LDG|LDS|LDL|STL|STS)\b", text)
+    assert len(re.findall(r"\bSTG\b", text)) == 3          # one unit sum: three doubles
+    assert re.search(r"\bDFMA\b", text) and re.search(r"c\[0x0\]\[", text)
+    assert len(body) * 16 <= 32 * 1024, len(body) * 16
