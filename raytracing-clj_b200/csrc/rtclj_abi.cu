@@ -490,7 +490,8 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
       std::memcpy(P.ctab, c->prim_geom, sizeof c->prim_geom);
       const unsigned long long want = (total_units + kPrimaryThreads - 1) / kPrimaryThreads;
       const unsigned blocks = (unsigned)std::min<unsigned long long>(want, (unsigned long long)grid * (unsigned long long)(2048 / kPrimaryThreads));
-      render_primary_kernel<<<blocks, kPrimaryThreads, 0, stream>>>(P);
+      if (P.use_defocus) render_primary_kernel<true><<<blocks, kPrimaryThreads, 0, stream>>>(P);
+      else render_primary_kernel<false><<<blocks, kPrimaryThreads, 0, stream>>>(P);
     } else if (wave) {
       P.stack_stride = (unsigned)grid * (unsigned)kWS;
       if (prm->max_depth > 1) {  // the attenuating hits of a path, for either product order

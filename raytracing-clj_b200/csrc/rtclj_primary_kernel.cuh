@@ -21,13 +21,14 @@ constexpr int kPrimarySpheres = 6;    // the measured crossover of scan vs cull 
 #define RTCLJ_PRIM_THREADS 256
 #endif
 #ifndef RTCLJ_PRIM_MINB
-#define RTCLJ_PRIM_MINB 4
+#define RTCLJ_PRIM_MINB 3
 #endif
 #ifndef RTCLJ_PRIM_UNROLL
 #define RTCLJ_PRIM_UNROLL 1
 #endif
 constexpr int kPrimaryThreads = RTCLJ_PRIM_THREADS;
 
+template <bool kDefocus>  // (as a run-time branch the unused disk draw still costs its conversions: 3 % of a sample)
 __global__ void __launch_bounds__(kPrimaryThreads, RTCLJ_PRIM_MINB) render_primary_kernel(const __grid_constant__ KParams P) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(kPrimaryThreads, RTCLJ_PRIM_MINB) render_prima
       const double sy = (double)pj + (u24(w.y) - 0.5);
       const d3 ps = add(add(ld3(P.p00), muls(ld3(P.du), sx)), muls(ld3(P.dv), sy));
       d3 O = ld3(P.center);
-      if (P.use_defocus) {  // vec3a/random-in-unit-disk, vec3a.clj:81-86
+      if (kDefocus) {  // vec3a/random-in-unit-disk, vec3a.clj:81-86
         double px = sym24(w.z), py = sym24(w.w);
         unsigned block = 0;
         int half = 1;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kPrimaryThreads, RTCLJ_PRIM_MINB) render_prima
           root = div_by(h + sq, a, ya, a_ok);
           if (root <= 1e-3) continue;
         }
-        if (root < closest || (root == closest && i < best)) { closest = root; best = i; }
+        if (root < closest) { closest = root; best = i; }  // list order: on an exact tie the earlier sphere stays
       }
 
       // ---- colour of the sample
