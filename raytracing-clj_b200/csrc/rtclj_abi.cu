@@ -246,6 +246,8 @@ int rtclj_ctx_create(int32_t device, rtclj_ctx** out) {
   CU(cudaFuncSetAttribute(render_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   CU(cudaFuncSetAttribute(render_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   CU(cudaFuncSetAttribute(render_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  CU(cudaFuncSetAttribute(render_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  CU(cudaFuncSetAttribute(render_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   CU(cudaFuncSetAttribute(render_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WaveSmem::total));
   CU(cudaFuncSetAttribute(render_lane2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lane2Smem::total));
   CU(cudaFuncSetAttribute(render_lane2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lane2Smem::total));
@@ -542,7 +544,10 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
         P.stack = c->stack.p;
       }
       const size_t sm = smem_needed(c->nhalf, const_tab, c->smem_optin);
-      if (const_tab && sample_buf) render_kernel<true, true><<<grid, threads_of(true), sm, stream>>>(P);
+      const bool packed = RTCLJ_PACKED_CANDS && c->n < 64;  // (measured per regime: rtclj_kernels.cuh, render_kernel)
+      if (const_tab && sample_buf && packed) render_kernel<true, true, true><<<grid, threads_of(true), sm, stream>>>(P);
+      else if (const_tab && packed) render_kernel<true, false, true><<<grid, threads_of(true), sm, stream>>>(P);
+      else if (const_tab && sample_buf) render_kernel<true, true><<<grid, threads_of(true), sm, stream>>>(P);
       else if (const_tab) render_kernel<true, false><<<grid, threads_of(true), sm, stream>>>(P);
       else if (sample_buf) render_kernel<false, true><<<grid, threads_of(false), sm, stream>>>(P);
       else render_kernel<false, false><<<grid, threads_of(false), sm, stream>>>(P);

@@ -69,8 +69,10 @@ __device__ __forceinline__ void path_step(const KParams& P, PathRegs& pr, PathCo
       const float tmin_lo = 1e-3f * vw.len32 * (1.0f - 16.0f * kEps32);
       const double ya = recip_refined(a);
       const bool a_ok = recip_safe(a);
+#if !RTCLJ_PACKED_CANDS
       int c1 = -1, c2 = -1, c3 = -1;
-      float lo1 = 3.0e38f, lo2 = 3.0e38f, lo3 = 3.0e38f;
+#endif
+      float lo1 = kCandEmpty, lo2 = kCandEmpty, lo3 = kCandEmpty;  // candidates (packed keys, rtclj_kernels.cuh)
       unsigned cur = 0, any = bany;
       int bbase = 0;
       const int nb_shift = 32 - P.nconst;
@@ -100,9 +102,16 @@ __device__ __forceinline__ void path_step(const KParams& P, PathRegs& pr, PathCo
         const float clo_hi = __double2float_ru(closest) * vw.len32 * (1.0f + 16.0f * kEps32);
         if (far_hi < tmin_lo || lo > clo_hi) continue;
         // keep the three candidates with the smallest lower bounds, sorted; a fourth is tested on the spot
+#if RTCLJ_PACKED_CANDS
+        {
+          const float out = cand_insert(cand_key(lo, i), lo1, lo2, lo3);
+          i = out < 1.0e38f ? cand_index(out) : -1;
+        }
+#else
         if (lo < lo1) { const int ti = c1; const float tl = lo1; c1 = i; lo1 = lo; i = ti; lo = tl; }
         if (i >= 0 && lo < lo2) { const int ti = c2; const float tl = lo2; c2 = i; lo2 = lo; i = ti; lo = tl; }
         if (i >= 0 && lo < lo3) { const int ti = c3; const float tl = lo3; c3 = i; lo3 = lo; i = ti; lo = tl; }
+#endif
         if (i >= 0) {  // (very rare)
           const HitPick hp = exact_test_lex_ni(P.geom64, i, O, D, a, ya, a_ok, closest, best);
           closest = hp.closest; best = hp.best; n_exact++;
@@ -110,8 +119,12 @@ __device__ __forceinline__ void path_step(const KParams& P, PathRegs& pr, PathCo
       }
 #pragma unroll 1
       for (int s2 = 0; s2 < 3; ++s2) {  // one inlined test site; the others only while their bound allows a win
-        const int ci = s2 == 0 ? c1 : (s2 == 1 ? c2 : c3);
         const float lo_i = s2 == 0 ? lo1 : (s2 == 1 ? lo2 : lo3);
+#if RTCLJ_PACKED_CANDS
+        const int ci = lo_i < 1.0e38f ? cand_index(lo_i) : -1;
+#else
+        const int ci = s2 == 0 ? c1 : (s2 == 1 ? c2 : c3);
+#endif
         if (ci < 0) break;
         if (s2 && !(lo_i <= __double2float_ru(closest) * vw.len32 * (1.0f + 16.0f * kEps32))) break;
         exact_test_lex(P.geom64, ci, O, D, a, ya, a_ok, closest, best);  // (out of line it costs 2.8 % of a bench frame)
