@@ -2,6 +2,7 @@
 # validation of a build: smoke, full GPU suite, fuzz soak, bench lines (default, lane kernel, c1, c2, c4), short renders
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
+[ -x ./gpurun_div_check ] && { timeout 200 ./gpurun_div_check | tee gpurun_out/am_div_check.log; }
 timeout 180 python __graft_entry__.py smoke > gpurun_out/am_smoke.log 2>&1 || { echo 'SMOKE FAILED'; tail -n 5 gpurun_out/am_smoke.log; exit 1; }
 timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/am_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/am_pytest.log
 tail -n 3 gpurun_out/am_pytest.log
