@@ -11,8 +11,10 @@ namespace rtclj {
 
 // out of line: the kernels that include this must stay inside the 32 KB instruction cache
 __device__ __noinline__ d3 lane2_divs_by(d3 v, double d) { return divs_by(v, d); }
-#ifndef RTCLJ_LANE2_PHILOX
-#define RTCLJ_LANE2_PHILOX philox_ni
+// the step's merged Philox call: inline with the host's round keys (46 instructions; the out-of-line copy with
+// its own key schedule is 60 + the call)
+#ifndef RTCLJ_LANE2_PHILOX_INLINE
+#define RTCLJ_LANE2_PHILOX_INLINE 1
 #endif
 
 // fp32 view of a ray for the conservative cull (coordinates translated by -shift); DESIGN.md "cull error bound"
@@ -158,7 +160,11 @@ __device__ __forceinline__ void path_step(const KParams& P, PathRegs& pr, PathCo
     double cx = 0.0, cy = 0.0, cz = 0.0, l2 = 1.0, schlick_u = 0.0;
     const bool next_cam = kind == K_MISS && k + 1 < k_end;
     if (kind >= 0 || next_cam) {
-      wq = RTCLJ_LANE2_PHILOX(pixel, (unsigned)k + (next_cam ? 1u : 0u), next_cam ? 0u : stage, 0u, P.k0, P.k1);
+#if RTCLJ_LANE2_PHILOX_INLINE
+      wq = RTCLJ_PHILOX(P, pixel, (unsigned)k + (next_cam ? 1u : 0u), next_cam ? 0u : stage, 0u);
+#else
+      wq = philox_ni(pixel, (unsigned)k + (next_cam ? 1u : 0u), next_cam ? 0u : stage, 0u, P.k0, P.k1);
+#endif
       have_wq = next_cam;
     }
     if (kind >= 0) {

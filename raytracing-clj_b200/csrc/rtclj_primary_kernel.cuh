@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kPrimaryThreads, RTCLJ_PRIM_MINB) render_prima
 #pragma unroll 1
     for (int k = chunk * P.spu; k < k_end; ++k) {
       // ---- camera ray: raytracing.clj:144-151, realm/raytracing.clj:332-339, raytracing_i.clj:150-158
-      uint4 w = philox(pixel, (unsigned)k, 0u, 0u, P.k0, P.k1);
+      uint4 w = RTCLJ_PHILOX(P, pixel, (unsigned)k, 0u, 0u);
       const double sx = (double)pi + (u24(w.x) - 0.5);
       const double sy = (double)pj + (u24(w.y) - 0.5);
       const d3 ps = add(add(ld3(P.p00), muls(ld3(P.du), sx)), muls(ld3(P.dv), sy));
