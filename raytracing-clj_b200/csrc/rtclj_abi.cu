@@ -108,9 +108,9 @@ int smem_table_blocks(size_t smem_optin) {
   const size_t fixed = (size_t)kListCap * threads_of(false) * 4 + 16 + (size_t)threads_of(false) * 24;
   return smem_optin > fixed ? (int)((smem_optin - fixed) / 512) : 0;
 }
-size_t smem_needed(int nhalf, bool const_tab, size_t smem_optin) {
+size_t smem_needed(int nhalf, bool const_tab, size_t smem_optin, bool few = false) {
   const size_t table = const_tab ? 0 : std::min((size_t)nhalf * 256, (size_t)smem_table_blocks(smem_optin) * 512);
-  const size_t threads = (size_t)threads_of(const_tab);
+  const size_t threads = (size_t)threads_of(const_tab, few);
   const size_t lists = (size_t)(const_tab ? 33 : kListCap) * threads * 4;
   return table + lists + 16 + threads * 24;
 }
@@ -539,15 +539,17 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
       }
 #endif
     } else {
-      P.stack_stride = (unsigned)grid * (unsigned)threads_of(const_tab);
+      // scenes of fewer than 64 spheres: their own instantiation (packed prefilter candidates, 768 threads), measured
+      // per regime -- rtclj_kernels.cuh, render_kernel / threads_of
+      const bool packed = RTCLJ_PACKED_CANDS && const_tab && c->n < 64;
+      P.stack_stride = (unsigned)grid * (unsigned)threads_of(const_tab, packed);
       if (prm->flags & RTCLJ_F_REVERSE_PRODUCT) {
         CU(c->stack.reserve((size_t)prm->max_depth * P.stack_stride));
         P.stack = c->stack.p;
       }
-      const size_t sm = smem_needed(c->nhalf, const_tab, c->smem_optin);
-      const bool packed = RTCLJ_PACKED_CANDS && c->n < 64;  // (measured per regime: rtclj_kernels.cuh, render_kernel)
-      if (const_tab && sample_buf && packed) render_kernel<true, true, true><<<grid, threads_of(true), sm, stream>>>(P);
-      else if (const_tab && packed) render_kernel<true, false, true><<<grid, threads_of(true), sm, stream>>>(P);
+      const size_t sm = smem_needed(c->nhalf, const_tab, c->smem_optin, packed);
+      if (const_tab && sample_buf && packed) render_kernel<true, true, true><<<grid, threads_of(true, true), sm, stream>>>(P);
+      else if (const_tab && packed) render_kernel<true, false, true><<<grid, threads_of(true, true), sm, stream>>>(P);
       else if (const_tab && sample_buf) render_kernel<true, true><<<grid, threads_of(true), sm, stream>>>(P);
       else if (const_tab) render_kernel<true, false><<<grid, threads_of(true), sm, stream>>>(P);
       else if (sample_buf) render_kernel<false, true><<<grid, threads_of(false), sm, stream>>>(P);
