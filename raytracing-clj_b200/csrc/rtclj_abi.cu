@@ -403,7 +403,9 @@ int rtclj_ctx_render(rtclj_ctx* c, const rtclj_camera* cam, const rtclj_params* 
   // cover scene 1920x1080: 500 spp 543.7 vs 561.6 ms, one eighth of it (an 8-GPU shard, 1.3e8 samples) 70.85 vs
   // 71.40 ms, 16 spp (3.3e7 samples) 19.6 vs 18.6 ms; 5 spheres: 11.7 vs 11.0 ms.  Break-even near 9e7 samples.
   const double total_samples = (double)local_pixels * (double)prm->spp;
-  int small = (c->n >= 64 && total_samples >= 1.0e8) ? SMALL_LANE2 : SMALL_LANE1;
+  // (final build of round 2, 16 / 24 / 32 / 48 spp at 1920x1080: 18.48 / 26.71 / 34.86 / 51.25 against 18.50 / 27.23 /
+  // 35.77 / 53.28 ms -- the break-even moved down to 3.3e7 samples; at 2e6 samples the single-path kernel is 30 % faster)
+  int small = (c->n >= 64 && total_samples >= 4.0e7) ? SMALL_LANE2 : SMALL_LANE1;
 #ifdef RTCLJ_DEFAULT_SMALL_KERNEL
   small = RTCLJ_DEFAULT_SMALL_KERNEL;
 #endif

@@ -69,4 +69,5 @@ if __name__ == "__main__":
         if only and name != only:
             continue
         world, cam, spp, *fl = mk()
+        spp = int(os.environ.get("RTCLJ_QP_SPP", spp))
         run(name, world, cam, spp, 50, fl[0] if fl else _abi.FLAGS_MAIN, reps=reps)
