@@ -82,8 +82,11 @@ enum {
                                    rays are traced, where it is faster) */
   RTCLJ_F_SMEM_TABLE = 1u << 17, /* testing: use the shared-memory-table kernel even for a small scene */
   /* Scenes of <= 512 spheres have four kernels that produce the same image; these select one
-   * explicitly (A/B timing, tests).  Without them the library uses the fastest one measured on the
-   * bench workload. */
+   * explicitly (A/B timing, tests).  Without them the library uses the fastest one measured for the
+   * regime (DESIGN.md sections 4 and 7): two paths per lane for >= 64 spheres and >= 4e7 samples per
+   * shard, one path per lane otherwise (its own instantiation below 64 spheres), and for primary-ray
+   * renders (RTCLJ_F_NORMAL_SHADING or max_depth 1) of <= 6 spheres a kernel without the path
+   * machinery.  RTCLJ_F_LANE_KERNEL also keeps such a render on the general kernel. */
   RTCLJ_F_LANE_KERNEL = 1u << 18,  /* one path per lane (round 1)                                   */
   RTCLJ_F_WAVE_KERNEL = 1u << 19,  /* wavefront kernel: path state in shared memory, per-phase queues */
   RTCLJ_F_LANE2_KERNEL = 1u << 20, /* two paths per lane, culled together                            */
