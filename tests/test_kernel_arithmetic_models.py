@@ -100,3 +100,103 @@ def test_zero_numerator_on_the_fast_path_has_the_quotients_sign():
         for d in (3.0, -3.0, 1e-300, -1e300):
             y = 1.0 / d                                        # any value with the sign of d
             assert np.signbit(n * y) == np.signbit(np.float64(n) / np.float64(d))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The conservative fp32 cull and the fp32 root prefilter (DESIGN.md "cull error bound"), restated in numpy: host
+# side of the table = rtclj_abi.cu rtclj_ctx_set_scene, device side = make_view / the cull block / the prefilter of
+# rtclj_kernels.cuh and rtclj_path_step.cuh.  Checked against the reference's own double arithmetic
+# (hittable.clj:9-23): a sphere the reference can hit is never culled and never dropped by the prefilter.
+def fma32(a, b, c):
+    """fmaf: the product of two float32 is exact in float64; the sum's double rounding is far below the margins"""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(F32)
+
+
+EPS32 = F32(2.0 ** -24)
+
+
+def round_up_f32(v):
+    f = v.astype(F32)
+    return np.where(f.astype(np.float64) < v, np.nextafter(f, F32(np.inf)), f)
+
+
+def cull_model(C, r, O, D, rng):
+    """Returns per (ray, sphere): dd (conservative discriminant), far_hi, lo, and per ray tmin_lo, len32."""
+    shift = np.median(C, axis=0) if len(C) % 2 else np.sort(C, axis=0)[len(C) // 2]     # nth_element(n / 2)
+    c32 = (C - shift).astype(F32)                                                      # (n, 3)
+    c2 = (c32.astype(np.float64) ** 2).sum(1)
+    eps = float(EPS32)
+    ws = round_up_f32(r * r * (1.0 + 8.0 * eps) - c2 * (1.0 - 96.0 * eps))            # (n,)
+    of = (O - shift).astype(F32)                                                       # (m, 3)
+    df = D.astype(F32)
+    l2 = (df[:, 0] * df[:, 0] + df[:, 1] * df[:, 1]) + df[:, 2] * df[:, 2]             # fp32, unfused
+    inv = (1.0 / np.sqrt(l2.astype(np.float64))).astype(F32)
+    inv = np.nextafter(inv, np.where(rng.random(len(inv)) < 0.5, F32(0), F32(np.inf)))  # rsqrt.approx: up to 2 ulp off
+    inv = np.nextafter(inv, np.where(rng.random(len(inv)) < 0.5, F32(0), F32(np.inf)))
+    dh = df * inv[:, None]
+    len32 = l2 * inv
+    mo = np.abs(of).max(1)
+    nbeta = -fma32(of[:, 2], dh[:, 2], fma32(of[:, 1], dh[:, 1], of[:, 0] * dh[:, 0]))
+    kq = fma32(of[:, 2], of[:, 2], fma32(of[:, 1], of[:, 1], of[:, 0] * of[:, 0])) * -(F32(1.0) - F32(96.0) * EPS32)
+    cx, cy, cz = (c32[None, :, k] for k in range(3))
+    bb = fma32(cz, dh[:, 2:3], fma32(cy, dh[:, 1:2], fma32(cx, dh[:, 0:1], nbeta[:, None] + F32(0) * cx)))
+    two = F32(2.0)
+    ss = fma32(cz, two * of[:, 2:3], fma32(cy, two * of[:, 1:2], fma32(cx, two * of[:, 0:1], ws[None, :] + kq[:, None])))
+    dd = fma32(bb, bb, ss)
+    sq = np.sqrt(np.maximum(dd, F32(0)).astype(np.float64)).astype(F32)
+    sq = np.nextafter(sq, np.where(rng.random(sq.shape) < 0.5, F32(0), F32(np.inf)))    # sqrt.approx
+    sq = sq * (F32(1.0) + F32(16.0) * EPS32)
+    eb = EPS32 * (F32(24.0) * (np.abs(cx) + np.abs(cy) + np.abs(cz)) + F32(40.0) * mo[:, None])
+    far_hi = bb + sq + eb
+    lo = bb - sq - eb
+    tmin_lo = F32(1e-3) * len32 * (F32(1.0) - F32(16.0) * EPS32)
+    return dd, far_hi, lo, tmin_lo, len32
+
+
+def reference_roots(C, r, O, D):
+    """hittable.clj:9-23 in double: near and far root per (ray, sphere), NaN where the discriminant is negative."""
+    oc = C[None, :, :] - O[:, None, :]
+    a = (D * D).sum(1)[:, None]
+    h = (D[:, None, :] * oc).sum(2)
+    c = (oc * oc).sum(2) - (r * r)[None, :]
+    disc = h * h - a * c
+    with np.errstate(invalid="ignore"):
+        sq = np.sqrt(disc)
+    return (h - sq) / a, (h + sq) / a, disc
+
+
+def test_fp32_cull_and_prefilter_never_drop_a_sphere_the_reference_can_hit():
+    rng = np.random.default_rng(20261019)
+    checked_hits = 0
+    for case in range(200):
+        n, m = int(rng.integers(1, 40)), 400
+        scale = 10.0 ** rng.uniform(-2, 4)
+        C = rng.normal(0, scale, (n, 3)) + rng.normal(0, scale * 3, 3)
+        r = np.abs(rng.normal(0, scale * 0.3, n)) + scale * 1e-3
+        if case % 3 == 0:
+            r[0] = scale * 1000.0; C[0] = [0.0, -r[0], 0.0]                         # a ground sphere
+        if case % 5 == 0:
+            r[-1] = -r[-1]                                                          # the inner bubble's negative radius
+        kind = case % 4
+        O = rng.normal(0, scale * (0.1, 1.0, 5.0, 30.0)[kind], (m, 3)) + C[rng.integers(0, n, m)] * (kind < 2)
+        D = rng.normal(0, 1, (m, 3)) * 10.0 ** rng.uniform(-3, 3, (m, 1))           # the reference never normalises d
+        j = rng.integers(0, n, m // 2)                                              # half of the rays start ON a sphere
+        u = rng.normal(0, 1, (m // 2, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+        O[: m // 2] = C[j] + u * np.abs(r[j])[:, None]
+        dd, far_hi, lo, tmin_lo, len32 = cull_model(C, r, O, D, rng)
+        near, far, disc = reference_roots(C, r, O, D)
+        can_hit = (disc >= 0.0) & ((near > 1e-3) | (far > 1e-3))                    # the reference would accept a root
+        checked_hits += int(can_hit.sum())
+        # (1) the cull: D' < 0 proves a miss
+        assert not np.any(can_hit & (dd < 0)), case
+        # (2) the prefilter's first rejection: the far root certainly at or below t_min
+        rej_far = far_hi < tmin_lo[:, None]
+        assert not np.any(can_hit & (dd >= 0) & rej_far), case
+        # (3) its bounds: lo <= root * |d| <= far_hi for the root the reference accepts
+        root = np.where(near > 1e-3, near, far)
+        arc = root * np.sqrt((D * D).sum(1))[:, None]
+        ok = can_hit & (dd >= 0)
+        slack = 1.0 + 16.0 * float(EPS32)
+        assert np.all(lo[ok].astype(np.float64) <= arc[ok] * slack + 1e-300), case
+        assert np.all(far_hi[ok].astype(np.float64) * slack >= arc[ok]), case
+    assert checked_hits > 40_000
