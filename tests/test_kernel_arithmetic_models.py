@@ -200,3 +200,17 @@ def test_fp32_cull_and_prefilter_never_drop_a_sphere_the_reference_can_hit():
         assert np.all(lo[ok].astype(np.float64) <= arc[ok] * slack + 1e-300), case
         assert np.all(far_hi[ok].astype(np.float64) * slack >= arc[ok]), case
     assert checked_hits > 40_000
+
+
+def test_symmetric_uniforms_in_one_conversion_equal_the_reference_form_for_every_input():
+    """rtclj_kernels.cuh sym21 / sym24: (f - 2^20) 2^-20 and ((w >> 8) - 2^23) 2^-23 against the oracle's form
+    -1 + 2 u with u = f 2^-21 / (w >> 8) 2^-24 (vec3a.clj:71-79 `rand-double -1 1` on the shim's uniforms) --
+    EVERY 21-bit field and EVERY 24-bit value, bit patterns included (the midpoint must be +0.0)."""
+    f = np.arange(1 << 21, dtype=np.int64)
+    a = (f - (1 << 20)).astype(np.float64) * (1.0 / (1 << 20))
+    b = -1.0 + 2.0 * (f.astype(np.float64) * (1.0 / (1 << 21)))
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    w = np.arange(1 << 24, dtype=np.int64)
+    a = (w - (1 << 23)).astype(np.float64) * (1.0 / (1 << 23))
+    b = -1.0 + 2.0 * (w.astype(np.float64) * (1.0 / (1 << 24)))
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
