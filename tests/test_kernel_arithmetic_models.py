@@ -214,3 +214,42 @@ def test_symmetric_uniforms_in_one_conversion_equal_the_reference_form_for_every
     a = (w - (1 << 23)).astype(np.float64) * (1.0 / (1 << 23))
     b = -1.0 + 2.0 * (w.astype(np.float64) * (1.0 / (1 << 24)))
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_list_scan_with_strict_bounds_equals_the_lexicographic_minimum():
+    """hit-anything (raytracing.clj:33-43) scans the list passing closest-so-far as t-max, with strict bounds in the
+    sphere test (hittable.clj:15-21).  The kernels resolve cull survivors in ANY order as the lexicographic minimum
+    of (root_i, i), root_i = the near root if it exceeds t-min, else the far root if that does (exact_test_lex).
+    Equivalence on random root sets drawn from a few values, so that exact ties are frequent."""
+    rng = np.random.default_rng(5)
+    tmin = 1e-3
+    vals = np.array([-2.0, 0.0, 5e-4, 1e-3, 2e-3, 0.5, 0.5, 1.0, 3.0])
+    for _ in range(20_000):
+        n = int(rng.integers(1, 7))
+        near = rng.choice(vals, n)
+        far = np.maximum(near, rng.choice(vals, n))          # near <= far
+        miss = rng.random(n) < 0.3                           # negative discriminant
+        # the reference: sequential, strict bounds, first body wins an exact tie
+        closest, best = np.inf, -1
+        for i in range(n):
+            if miss[i]:
+                continue
+            root = near[i]
+            if root <= tmin or closest <= root:
+                root = far[i]
+                if root <= tmin or closest <= root:
+                    continue
+            closest, best = root, i
+        # the kernels: any order (here: reversed), lexicographic minimum
+        c2, b2 = np.inf, -1
+        for i in reversed(range(n)):
+            if miss[i]:
+                continue
+            root = near[i]
+            if root <= tmin:
+                root = far[i]
+                if root <= tmin:
+                    continue
+            if root < c2 or (root == c2 and i < b2):
+                c2, b2 = root, i
+        assert (closest, best) == (c2, b2), (near, far, miss)
