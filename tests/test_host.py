@@ -147,6 +147,28 @@ def test_ppm_reader_round_trip_and_rejections(tmp_path):
     assert np.array_equal(np.asarray(Image.open(dst).convert("RGB")), gold)
 
 
+def test_large_ppm_bodies_are_parsed_by_several_threads_with_the_same_results_and_errors():
+    """Bodies of >= 4 MB (a 4K scene.ppm has 99 MB) go through the threaded parser; anything unusual falls back
+    to the sequential one, so results and rejections are those of small inputs."""
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, size=(900, 1200, 3), dtype=np.uint8)
+    img[:300] = 0; img[300:600] = 255                       # one-digit and three-digit stretches: uneven token density
+    text = render.encode_ppm(img)
+    assert len(text) > (4 << 20)
+    assert np.array_equal(render.decode_ppm(text), img)
+    assert np.array_equal(render.decode_ppm(text.replace(b"\n", b"\r\n  ").replace(b" ", b"\t ")), img)   # other white space
+    body = text.index(b"255\n") + 4
+    mid = body + (len(text) - body) // 2
+    mid = text.index(b"\n", mid) + 1
+    for bad in (text + b"7\n",                                          # one value too many
+                text[: text.rindex(b" ")] + b"\n",                      # one value missing
+                text[:mid] + b"300 " + text[text.index(b" ", mid) + 1:],  # a value above the maximum, deep in the body
+                text[:mid] + b"x" + text[mid + 1:],                      # not a digit
+                text[:mid] + b"1.5 " + text[text.index(b" ", mid) + 1:]):
+        with pytest.raises(_abi.RtcljError):
+            render.decode_ppm(bad)
+
+
 def test_png_encoder_decodes_to_the_same_pixels():
     import io
     from PIL import Image
