@@ -147,6 +147,25 @@ def test_ppm_reader_round_trip_and_rejections(tmp_path):
     assert np.array_equal(np.asarray(Image.open(dst).convert("RGB")), gold)
 
 
+def test_large_images_are_written_by_several_threads_byte_for_byte_like_small_ones():
+    """rtclj_encode_ppm_p3 writes images of >= 2^18 pixels with several threads (measure, then write at offsets):
+    the text must be the bytes the one-thread loop writes -- checked against Python's own formatting, with exact
+    and with generous capacity."""
+    import ctypes as C
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, size=(700, 900, 3), dtype=np.uint8)
+    img[:100] = 7; img[100:200] = 200; img[-1, -3:] = [[0, 0, 0], [255, 255, 255], [9, 99, 100]]
+    want = b"P3\n900 700\n255\n" + b"".join(b"%d %d %d\n" % (r, g, b) for r, g, b in img.reshape(-1, 3).tolist())
+    assert render.encode_ppm(img) == want
+    lib = _abi.lib()
+    n = C.c_size_t()
+    exact = C.create_string_buffer(len(want))                       # exactly as many bytes as the text needs
+    _abi.check(lib.rtclj_encode_ppm_p3(img.ctypes.data, 900, 700, exact, len(want), C.byref(n)))
+    assert n.value == len(want) and exact.raw == want
+    short = C.create_string_buffer(len(want) - 1)
+    assert lib.rtclj_encode_ppm_p3(img.ctypes.data, 900, 700, short, len(want) - 1, C.byref(n)) == _abi.E_BUFFER and n.value == len(want)
+
+
 def test_large_ppm_bodies_are_parsed_by_several_threads_with_the_same_results_and_errors():
     """Bodies of >= 4 MB (a 4K scene.ppm has 99 MB) go through the threaded parser; anything unusual falls back
     to the sequential one, so results and rejections are those of small inputs."""
