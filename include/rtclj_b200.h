@@ -243,7 +243,8 @@ int rtclj_calibrate_peaks(int32_t device, double *ffma_tflops, double *ffma2_tfl
 int rtclj_quantise_rgb8(const double *linear, size_t n_values, uint32_t flags, uint8_t *out);
 
 /* "P3\nW H\n255\n" + one "r g b\n" line per pixel.  Call with out == NULL to get a sufficient
- * capacity (an upper bound) in *len; the full call sets *len to the bytes written. */
+ * capacity (an upper bound) in *len; the full call sets *len to the bytes written.  Images of 2^18
+ * pixels and more are written by several short-lived host threads (half of the cores, at most 16). */
 int rtclj_encode_ppm_p3(const uint8_t *rgb8, int32_t width, int32_t height, char *out,
                         size_t capacity, size_t *len);
 
@@ -271,7 +272,8 @@ int rtclj_encode_png(const uint8_t *rgb8, int32_t width, int32_t height, uint8_t
  * "r g b" line per pixel; this parser accepts any whitespace between the tokens).  Call with
  * out_rgb8 == NULL to get the dimensions; RTCLJ_E_INVALID for a malformed file (bad magic, bad
  * dimensions, maximum outside 0..255, a component outside 0..max, too few or too many values),
- * RTCLJ_E_BUFFER if capacity < 3*W*H. */
+ * RTCLJ_E_BUFFER if capacity < 3*W*H.  Bodies of 4 MB and more are parsed by several short-lived host
+ * threads (at most 16); results and errors are those of the one-thread parser. */
 int rtclj_decode_ppm_p3(const char *text, size_t len, int32_t *width, int32_t *height,
                         uint8_t *out_rgb8, size_t capacity);
 
