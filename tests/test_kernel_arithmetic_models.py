@@ -253,3 +253,21 @@ def test_list_scan_with_strict_bounds_equals_the_lexicographic_minimum():
             if root < c2 or (root == c2 and i < b2):
                 c2, b2 = root, i
         assert (closest, best) == (c2, b2), (near, far, miss)
+
+
+def test_tickets_visit_every_unit_once_from_the_last_pixel_to_the_first():
+    """rtclj_kernels.cuh unit_of_ticket(): ticket -> (local pixel, chunk) with a pixel's chunks on consecutive tickets
+    and the pixels handed out from the shard's last to its first (the top rows -- sky -- last, DESIGN.md section 6);
+    `unit` = pixel * nchunks + chunk addresses the unit sums."""
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        npix, nchunks = int(rng.integers(1, 400)), int(rng.integers(1, 21))
+        t = np.arange(npix * nchunks, dtype=np.uint32)
+        q = t // np.uint32(nchunks)
+        p_local = np.uint32(npix - 1) - q
+        unit = p_local * np.uint32(nchunks) + (t - q * np.uint32(nchunks))
+        assert np.array_equal(np.sort(unit), t)                          # a bijection onto the unit sums
+        assert np.array_equal(unit // nchunks, p_local)                  # what the kernels recover from `unit`
+        assert np.all(np.diff(p_local.astype(np.int64)) <= 0) and p_local[0] == npix - 1 and p_local[-1] == 0
+        same = p_local[1:] == p_local[:-1]
+        assert np.all((unit[1:] - unit[:-1])[same] == 1)                 # chunks of a pixel in order
